@@ -1,0 +1,806 @@
+// capi.cu — the C ABI (include/gorender_b200.h): context, asset upload,
+// workspace management and the per-draw orchestration that replaces the body
+// of (*Renderer).Draw (renderer.go:443-483).
+//
+// Host work per draw is what the reference also does once per object per
+// frame and is not per-vertex: BoxVisibility of the 8 bounding-box corners
+// (renderer.go:268-275, clipping.go:131-154).  Everything per-vertex,
+// per-face and per-pixel runs in the five kernels (kernels.h).  There is no
+// CPU rendering path in this library.
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gr_types.cuh"
+#include "kernels.h"
+
+using namespace gr;
+
+namespace {
+
+std::string g_createError;
+
+struct MeshHost {
+    bool live = false;
+    MeshDev dev{};
+    float bbox[32];
+    std::vector<void *> allocs;
+};
+
+struct TexHost {
+    TexDev dev{};
+    void *pixels = nullptr;
+};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+};
+
+constexpr int kStagingRing = 4;
+
+}  // namespace
+
+struct grb_framebuffer {
+    grb_context *ctx;
+    int32_t width, height, frames;
+    uchar4 *color;
+    float *depth;
+    bool owned;
+};
+
+struct grb_context {
+    int device = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    mutable std::string err;
+
+    std::vector<MeshHost> meshes;
+    DevBuf<MeshDev> dMeshes;
+    bool meshesDirty = true;
+    std::vector<TexHost> textures;
+    DevBuf<TexDev> dTextures;
+    bool texturesDirty = true;
+
+    // draw-list plan (same meshes => same tables)
+    std::vector<int32_t> planMeshes;
+    std::vector<DrawObj> planObjs;
+    DevBuf<DrawObj> dObjs;
+    DevBuf<int32_t> dVblk, dFblk;
+    int32_t nVertBlocks = 0, nFaceBlocks = 0, totalVerts = 0;
+    bool planValid = false;
+
+    // per-(frame,object) matrices: pinned staging ring + device copy
+    FrameObj *hFrameObjs[kStagingRing] = {};
+    size_t hFrameObjsCap[kStagingRing] = {};
+    cudaEvent_t stagingDone[kStagingRing] = {};
+    int stagingNext = 0;
+    DevBuf<FrameObj> dFrameObjs;
+
+    // workspace
+    DevBuf<float4> tv;
+    DevBuf<TriRec> rec;
+    DevBuf<TriUV> uv;
+    DevBuf<uint32_t> blockBase, tileCount, tileOff, cursor, binList, bigList;
+    DevBuf<FrameCounters> counters;
+    uint32_t recCap = 0;  // per frame
+
+    // last draw (for stats / debug read-backs)
+    int32_t lastFrames = 0, lastNobj = 0, lastNTiles = 0;
+    std::vector<int32_t> lastVisibility;
+
+    // seam scratch
+    DevBuf<float4> seam;
+
+    // timing
+    bool timing = false;
+    cudaEvent_t tev[6] = {};
+    double accMs[5] = {0, 0, 0, 0, 0};
+    int64_t accLaunches = 0;
+    int64_t totalLaunches = 0;
+};
+
+namespace {
+
+int32_t fail(const grb_context *ctx, int32_t code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_createError = msg;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            const int32_t code__ = (e__ == cudaErrorMemoryAllocation) ? GRB_ERR_OOM : GRB_ERR_CUDA;     \
+            return fail(ctx, code__, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+        }                                                                                               \
+    } while (0)
+
+// Grow a device buffer to at least n elements.  Old contents are dropped;
+// zero-filled when `zero`.  Synchronises the stream before freeing.
+template <typename T> int32_t ensure(grb_context *ctx, DevBuf<T> &b, size_t n, bool zero) {
+    if (n <= b.cap && b.p) return GRB_OK;
+    if (n == 0) n = 1;
+    if (b.p) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t grow = n + n / 4;
+    cudaError_t e = cudaMalloc(&b.p, grow * sizeof(T));
+    size_t got = grow;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, n * sizeof(T));
+        got = n;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        return fail(ctx, GRB_ERR_OOM, "cudaMalloc of " + std::to_string(n * sizeof(T)) + " bytes failed");
+    }
+    b.cap = got;
+    if (zero) CK(ctx, cudaMemsetAsync(b.p, 0, got * sizeof(T), ctx->stream));
+    return GRB_OK;
+}
+
+template <typename T> int32_t upload(grb_context *ctx, const T *src, size_t n, T **out, std::vector<void *> &allocs) {
+    *out = nullptr;
+    if (n == 0 || src == nullptr) return GRB_OK;
+    void *p = nullptr;
+    CK(ctx, cudaMalloc(&p, n * sizeof(T)));
+    allocs.push_back(p);
+    CK(ctx, cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<T *>(p);
+    return GRB_OK;
+}
+
+// Frustum.BoxVisibility (clipping.go:131-154) with the planes of
+// NewFrustum (clipping.go:93-126); Plane.DistanceToVertex (clipping.go:69-71).
+int box_visibility(const float4 corners[8], float zn, float zf) {
+    const float4 P[6] = {{-1, 0, 0, 1}, {1, 0, 0, 1}, {0, -1, 0, 1}, {0, 1, 0, 1}, {0, 0, zn, 1}, {0, 0, zf, 1}};
+    const float4 N[6] = {{1, 0, 0, 1}, {-1, 0, 0, 1}, {0, 1, 0, 1}, {0, -1, 0, 1}, {0, 0, -1, 0}, {0, 0, 1, 0}};
+    for (int i = 0; i < 6; i++) {
+        int outside = 0;
+        for (int c = 0; c < 8; c++)
+            if (fsub(dot4(N[i], corners[c]), dot4(N[i], P[i])) > 0.0f) outside++;
+        if (outside == 8) return GRB_BOX_OUTSIDE;
+        if (outside > 0) return GRB_BOX_INTERSECT;
+    }
+    return GRB_BOX_INSIDE;
+}
+
+int32_t sync_tables(grb_context *ctx) {
+    if (ctx->meshesDirty) {
+        std::vector<MeshDev> t(ctx->meshes.size());
+        for (size_t i = 0; i < t.size(); i++) t[i] = ctx->meshes[i].dev;
+        if (int32_t r = ensure(ctx, ctx->dMeshes, t.size(), false)) return r;
+        if (!t.empty())
+            CK(ctx, cudaMemcpyAsync(ctx->dMeshes.p, t.data(), t.size() * sizeof(MeshDev), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->meshesDirty = false;
+    }
+    if (ctx->texturesDirty) {
+        std::vector<TexDev> t(ctx->textures.size());
+        for (size_t i = 0; i < t.size(); i++) t[i] = ctx->textures[i].dev;
+        if (int32_t r = ensure(ctx, ctx->dTextures, t.size(), false)) return r;
+        if (!t.empty())
+            CK(ctx, cudaMemcpyAsync(ctx->dTextures.p, t.data(), t.size() * sizeof(TexDev), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->texturesDirty = false;
+    }
+    return GRB_OK;
+}
+
+int32_t build_plan(grb_context *ctx, const grb_object *objects, int32_t nobj) {
+    bool same = ctx->planValid && (int32_t)ctx->planMeshes.size() == nobj;
+    for (int32_t i = 0; same && i < nobj; i++) same = ctx->planMeshes[i] == objects[i].mesh;
+    if (same) return GRB_OK;
+
+    ctx->planValid = false;
+    ctx->planMeshes.resize(nobj);
+    ctx->planObjs.resize(nobj);
+    std::vector<int32_t> vblk, fblk;
+    int64_t verts = 0;
+    for (int32_t i = 0; i < nobj; i++) {
+        const MeshDev &m = ctx->meshes[objects[i].mesh].dev;
+        DrawObj &o = ctx->planObjs[i];
+        ctx->planMeshes[i] = objects[i].mesh;
+        o.mesh = objects[i].mesh;
+        o.vertBase = (int32_t)verts;
+        o.vertBlockBase = (int32_t)vblk.size();
+        o.faceBlockBase = (int32_t)fblk.size();
+        verts += m.nv;
+        vblk.insert(vblk.end(), (m.nv + 255) / 256, i);
+        fblk.insert(fblk.end(), (m.nf + kFaceBlock - 1) / kFaceBlock, i);
+    }
+    if (verts > INT32_MAX) return fail(ctx, GRB_ERR_INVALID, "draw list has more than 2^31 vertices");
+    if ((int64_t)fblk.size() * kSeqStride >= (int64_t)UINT32_MAX)
+        return fail(ctx, GRB_ERR_INVALID, "draw list has too many faces for 32-bit submission keys");
+    ctx->totalVerts = (int32_t)verts;
+    ctx->nVertBlocks = (int32_t)vblk.size();
+    ctx->nFaceBlocks = (int32_t)fblk.size();
+    if (int32_t r = ensure(ctx, ctx->dObjs, (size_t)nobj, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->dVblk, vblk.size(), false)) return r;
+    if (int32_t r = ensure(ctx, ctx->dFblk, fblk.size(), false)) return r;
+    // tables may still be in use by an in-flight draw
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nobj) CK(ctx, cudaMemcpy(ctx->dObjs.p, ctx->planObjs.data(), nobj * sizeof(DrawObj), cudaMemcpyHostToDevice));
+    if (!vblk.empty())
+        CK(ctx, cudaMemcpy(ctx->dVblk.p, vblk.data(), vblk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!fblk.empty())
+        CK(ctx, cudaMemcpy(ctx->dFblk.p, fblk.data(), fblk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->planValid = true;
+    return GRB_OK;
+}
+
+int32_t set_device(const grb_context *ctx) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, GRB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return GRB_OK;
+}
+
+int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, const grb_object *objects,
+                  int32_t nobj, const grb_draw_params *prm) {
+    if (!ctx || !fb || !prm) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
+    if (nframes <= 0 || frame0 < 0 || frame0 + nframes > fb->frames)
+        return fail(ctx, GRB_ERR_INVALID, "frame range outside the framebuffer");
+    if (nobj < 0 || (nobj > 0 && !objects)) return fail(ctx, GRB_ERR_INVALID, "bad object list");
+    if (prm->ref_tiles != 1 && prm->ref_tiles != 16)
+        return fail(ctx, GRB_ERR_INVALID, "ref_tiles must be 16 (parallel) or 1 (serial): renderer.go:144,151");
+    if (fb->width > kCoordLimit || fb->height > kCoordLimit)
+        return fail(ctx, GRB_ERR_INVALID, "framebuffer larger than 16383 pixels on a side");
+    for (int32_t i = 0; i < nobj; i++) {
+        const int32_t m = objects[i].mesh;
+        if (m < 0 || m >= (int32_t)ctx->meshes.size() || !ctx->meshes[m].live)
+            return fail(ctx, GRB_ERR_INVALID, "object " + std::to_string(i) + " refers to an unknown mesh");
+        for (int32_t f = 1; f < nframes; f++)
+            if (objects[(size_t)f * nobj + i].mesh != m)
+                return fail(ctx, GRB_ERR_INVALID, "all frames of a batch must draw the same meshes");
+    }
+    if (int32_t r = set_device(ctx)) return r;
+
+    const int ntx = (fb->width + kTile - 1) / kTile, nty = (fb->height + kTile - 1) / kTile;
+    int rowBegin = 0, rowEnd = nty;
+    if (!(prm->row_begin == 0 && prm->row_end == 0)) {
+        if (prm->row_begin < 0 || prm->row_end <= prm->row_begin || prm->row_begin % kTile ||
+            (prm->row_end % kTile && prm->row_end != fb->height) || prm->row_end > fb->height)
+            return fail(ctx, GRB_ERR_INVALID, "row range must be tile-aligned and inside the frame");
+        rowBegin = prm->row_begin / kTile;
+        rowEnd = (prm->row_end + kTile - 1) / kTile;
+    }
+
+    if (int32_t r = sync_tables(ctx)) return r;
+    if (int32_t r = build_plan(ctx, objects, nobj)) return r;
+
+    // ---- per (frame, object): matrices + BoxVisibility (renderer.go:268-275)
+    const size_t nfo = (size_t)nframes * std::max(nobj, 1);
+    const int ring = ctx->stagingNext;
+    ctx->stagingNext = (ring + 1) % kStagingRing;
+    if (ctx->hFrameObjsCap[ring] < nfo) {
+        if (ctx->hFrameObjs[ring]) {
+            CK(ctx, cudaEventSynchronize(ctx->stagingDone[ring]));
+            CK(ctx, cudaFreeHost(ctx->hFrameObjs[ring]));
+            ctx->hFrameObjs[ring] = nullptr;
+        }
+        CK(ctx, cudaHostAlloc((void **)&ctx->hFrameObjs[ring], nfo * sizeof(FrameObj), cudaHostAllocDefault));
+        ctx->hFrameObjsCap[ring] = nfo;
+    } else {
+        CK(ctx, cudaEventSynchronize(ctx->stagingDone[ring]));
+    }
+    FrameObj *hfo = ctx->hFrameObjs[ring];
+
+    const bool optClip = prm->options & GRB_OPT_FRUSTUM_CLIPPING;
+    bool anyPlain = false, anyClip = false;
+    uint64_t recNeed = 1;
+    ctx->lastVisibility.assign((size_t)nframes * nobj, GRB_BOX_OUTSIDE);
+    for (int32_t f = 0; f < nframes; f++) {
+        uint64_t need = 0;
+        for (int32_t i = 0; i < nobj; i++) {
+            const grb_object &src = objects[(size_t)f * nobj + i];
+            FrameObj &dst = hfo[(size_t)f * nobj + i];
+            std::memcpy(dst.mvp, src.mvp, 64);
+            std::memcpy(dst.world, src.world, 64);
+            const MeshHost &mh = ctx->meshes[src.mesh];
+            float4 corners[8];
+            for (int c = 0; c < 8; c++) {
+                const float4 p = make_float4(mh.bbox[4 * c], mh.bbox[4 * c + 1], mh.bbox[4 * c + 2], mh.bbox[4 * c + 3]);
+                corners[c] = mat_vec(src.mvp, p);  // matrixMultiplyVec4Batch(&mvpMatrix, bbox[:])
+            }
+            const int vis = box_visibility(corners, prm->z_near, prm->z_far);
+            dst.visibility = vis;
+            ctx->lastVisibility[(size_t)f * nobj + i] = vis;
+            if (vis == GRB_BOX_OUTSIDE) continue;
+            const bool clips = optClip && vis != GRB_BOX_INSIDE;
+            (clips ? anyClip : anyPlain) = true;
+            need += (uint64_t)mh.dev.nf * (clips ? kMaxFan : 1);
+        }
+        recNeed = std::max(recNeed, need);
+    }
+    if (recNeed * kMaxBinsPerTri > UINT32_MAX) return fail(ctx, GRB_ERR_INVALID, "too many triangles per frame");
+
+    // ---- workspace
+    const int nTiles = ntx * nty;
+    const uint32_t recCap = std::max<uint32_t>(ctx->recCap, (uint32_t)recNeed);
+    const size_t F = (size_t)nframes;
+    // a larger per-frame stride invalidates nothing that is live across draws except the zeroed tile counters
+    if (int32_t r = ensure(ctx, ctx->dFrameObjs, nfo, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->tv, F * std::max(ctx->totalVerts, 1), false)) return r;
+    if (int32_t r = ensure(ctx, ctx->rec, F * recCap, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->uv, F * recCap, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->bigList, F * recCap, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->binList, F * recCap * kMaxBinsPerTri, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->blockBase, F * std::max(ctx->nFaceBlocks, 1), false)) return r;
+    if (int32_t r = ensure(ctx, ctx->tileOff, F * (nTiles + 1), false)) return r;
+    if (int32_t r = ensure(ctx, ctx->cursor, F * nTiles, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->counters, F, false)) return r;
+    ctx->recCap = recCap;
+    // tile counters must be zero on entry; K3 re-zeroes what K2 counted, but the
+    // per-frame stride depends on nTiles, so clear when the geometry changes
+    if (ctx->tileCount.cap < F * nTiles || ctx->lastNTiles != nTiles) {
+        if (int32_t r = ensure(ctx, ctx->tileCount, F * nTiles, false)) return r;
+        CK(ctx, cudaMemsetAsync(ctx->tileCount.p, 0, ctx->tileCount.cap * sizeof(uint32_t), ctx->stream));
+    }
+
+    CK(ctx, cudaMemcpyAsync(ctx->dFrameObjs.p, hfo, nfo * sizeof(FrameObj), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->stagingDone[ring], ctx->stream));
+    CK(ctx, cudaMemsetAsync(ctx->counters.p, 0, F * sizeof(FrameCounters), ctx->stream));
+
+    DrawArgs a{};
+    a.meshes = ctx->dMeshes.p;
+    a.textures = ctx->dTextures.p;
+    a.ntex = (int32_t)ctx->textures.size();
+    a.objs = ctx->dObjs.p;
+    a.vblkObj = ctx->dVblk.p;
+    a.fblkObj = ctx->dFblk.p;
+    a.frameObjs = ctx->dFrameObjs.p;
+    a.nobj = nobj;
+    a.nVertBlocks = ctx->nVertBlocks;
+    a.nFaceBlocks = ctx->nFaceBlocks;
+    a.totalVerts = ctx->totalVerts;
+    a.tv = ctx->tv.p;
+    a.rec = ctx->rec.p;
+    a.uv = ctx->uv.p;
+    a.blockBase = ctx->blockBase.p;
+    a.tileCount = ctx->tileCount.p;
+    a.tileOff = ctx->tileOff.p;
+    a.cursor = ctx->cursor.p;
+    a.binList = ctx->binList.p;
+    a.bigList = ctx->bigList.p;
+    a.counters = ctx->counters.p;
+    a.recCap = recCap;
+    a.color = fb->color + (size_t)frame0 * fb->width * fb->height;
+    a.depth = fb->depth + (size_t)frame0 * fb->width * fb->height;
+    a.width = fb->width;
+    a.height = fb->height;
+    a.ntx = ntx;
+    a.nty = nty;
+    a.tileRowBegin = rowBegin;
+    a.tileRowEnd = rowEnd;
+    std::memcpy(a.screen.m, prm->screen, 64);
+    a.lx = prm->light[0]; a.ly = prm->light[1]; a.lz = prm->light[2];
+    a.options = prm->options;
+    a.zNear = prm->z_near;
+    a.zFar = prm->z_far;
+    if (prm->ref_tiles == 1) {
+        a.ref = {1, 1, fb->width, fb->height};
+    } else {
+        // calculateTileBoundaries (renderer.go:56-59) for numTiles = 16
+        const int n = 16, rtx = 4, rty = (n + rtx - 1) / rtx;
+        a.ref = {rtx, rty, (fb->width + rtx - 1) / rtx, (fb->height + rty - 1) / rty};
+    }
+
+    const bool anyVisible = anyPlain || anyClip;
+    cudaStream_t s = ctx->stream;
+    const bool tm = ctx->timing;
+    if (tm) CK(ctx, cudaEventRecord(ctx->tev[0], s));
+    if (anyVisible) launch_transform(a, nframes, s);
+    if (tm) CK(ctx, cudaEventRecord(ctx->tev[1], s));
+    if (anyVisible) launch_setup(a, nframes, anyPlain, anyClip, s);
+    if (tm) CK(ctx, cudaEventRecord(ctx->tev[2], s));
+    launch_bin_scan(a, nframes, s);
+    if (tm) CK(ctx, cudaEventRecord(ctx->tev[3], s));
+    if (anyVisible) launch_bin_fill(a, nframes, (uint32_t)recNeed, s);
+    if (tm) CK(ctx, cudaEventRecord(ctx->tev[4], s));
+    launch_raster(a, nframes, s);
+    if (tm) CK(ctx, cudaEventRecord(ctx->tev[5], s));
+    CK(ctx, cudaGetLastError());
+
+    int launches = 2;  // scan + raster
+    if (anyVisible) launches += 2 + (anyPlain ? 1 : 0) + (anyClip ? 1 : 0);
+    ctx->totalLaunches += launches;
+
+    if (tm) {
+        CK(ctx, cudaEventSynchronize(ctx->tev[5]));
+        for (int k = 0; k < 5; k++) {
+            float ms = 0;
+            CK(ctx, cudaEventElapsedTime(&ms, ctx->tev[k], ctx->tev[k + 1]));
+            ctx->accMs[k] += ms;
+        }
+        ctx->accLaunches += launches;
+    }
+
+    ctx->lastFrames = nframes;
+    ctx->lastNobj = nobj;
+    ctx->lastNTiles = nTiles;
+    return GRB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t grb_abi_version(void) { return GRB_ABI_VERSION; }
+
+const char *grb_last_error(const grb_context *ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int32_t grb_context_create(int32_t device, grb_context **out) {
+    if (!out) return fail(nullptr, GRB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, GRB_ERR_CUDA,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (this library has no CPU path)");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, GRB_ERR_INVALID, "device ordinal out of range");
+    grb_context *ctx = new grb_context;
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, GRB_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->ownStream;
+    for (int i = 0; i < kStagingRing; i++) cudaEventCreateWithFlags(&ctx->stagingDone[i], cudaEventDisableTiming);
+    for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->tev[i]);
+    *out = ctx;
+    return GRB_OK;
+}
+
+int32_t grb_context_destroy(grb_context *ctx) {
+    if (!ctx) return GRB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &m : ctx->meshes)
+        for (void *p : m.allocs) cudaFree(p);
+    for (auto &t : ctx->textures)
+        if (t.pixels) cudaFree(t.pixels);
+    void *bufs[] = {ctx->dMeshes.p, ctx->dTextures.p, ctx->dObjs.p, ctx->dVblk.p, ctx->dFblk.p, ctx->dFrameObjs.p,
+                    ctx->tv.p, ctx->rec.p, ctx->uv.p, ctx->blockBase.p, ctx->tileCount.p, ctx->tileOff.p,
+                    ctx->cursor.p, ctx->binList.p, ctx->bigList.p, ctx->counters.p, ctx->seam.p};
+    for (void *p : bufs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < kStagingRing; i++) {
+        if (ctx->hFrameObjs[i]) cudaFreeHost(ctx->hFrameObjs[i]);
+        if (ctx->stagingDone[i]) cudaEventDestroy(ctx->stagingDone[i]);
+    }
+    for (int i = 0; i < 6; i++)
+        if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+    return GRB_OK;
+}
+
+int32_t grb_context_set_stream(grb_context *ctx, void *cuda_stream) {
+    if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
+    if (int32_t r = set_device(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->ownStream;
+    return GRB_OK;
+}
+
+int32_t grb_context_synchronize(grb_context *ctx) {
+    if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
+    if (int32_t r = set_device(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int32_t grb_context_set_kernel_timing(grb_context *ctx, int32_t enable) {
+    if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
+    ctx->timing = enable != 0;
+    return GRB_OK;
+}
+
+int32_t grb_kernel_times(grb_context *ctx, double out_ms[5], int64_t *out_launches) {
+    if (!ctx || !out_ms) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    for (int k = 0; k < 5; k++) { out_ms[k] = ctx->accMs[k]; ctx->accMs[k] = 0; }
+    if (out_launches) *out_launches = ctx->accLaunches;
+    ctx->accLaunches = 0;
+    return GRB_OK;
+}
+
+int64_t grb_launch_count(const grb_context *ctx) { return ctx ? ctx->totalLaunches : 0; }
+
+void *grb_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void grb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int32_t grb_texture_upload(grb_context *ctx, int32_t type, int32_t width, int32_t height, float scale,
+                           const uint8_t color[4], const uint8_t *pixels, int32_t *out_id) {
+    if (!ctx || !out_id) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (int32_t r = set_device(ctx)) return r;
+    TexHost t;
+    t.dev.type = type;
+    t.dev.scale = scale;
+    t.dev.color = color ? make_uchar4(color[0], color[1], color[2], color[3]) : make_uchar4(0, 0, 0, 0);
+    if (type == GRB_TEX_SOLID) {
+        t.dev.width = t.dev.height = 0;
+    } else if (type == GRB_TEX_IMAGE || type == GRB_TEX_IMAGE_FAST) {
+        if (width <= 0 || height <= 0 || !pixels) return fail(ctx, GRB_ERR_INVALID, "image texture needs pixels");
+        if (type == GRB_TEX_IMAGE_FAST && ((width & (width - 1)) || (height & (height - 1))))
+            return fail(ctx, GRB_ERR_INVALID, "TextureTypeImageFast needs power-of-two sizes (texture.go:40-43)");
+        t.dev.width = width;
+        t.dev.height = height;
+        const size_t bytes = (size_t)width * height * 4;
+        CK(ctx, cudaMalloc(&t.pixels, bytes));
+        CK(ctx, cudaMemcpy(t.pixels, pixels, bytes, cudaMemcpyHostToDevice));
+        t.dev.pixels = static_cast<const uchar4 *>(t.pixels);
+    } else {
+        return fail(ctx, GRB_ERR_INVALID, "unknown texture type");
+    }
+    t.dev.widthF = (float)t.dev.width;   // texture.go:50-51
+    t.dev.heightF = (float)t.dev.height;
+    ctx->textures.push_back(t);
+    ctx->texturesDirty = true;
+    *out_id = (int32_t)ctx->textures.size() - 1;
+    return GRB_OK;
+}
+
+int32_t grb_texture_set_scale(grb_context *ctx, int32_t id, float scale) {
+    if (!ctx || id < 0 || id >= (int32_t)ctx->textures.size()) return fail(ctx, GRB_ERR_INVALID, "bad texture id");
+    ctx->textures[id].dev.scale = scale;
+    ctx->texturesDirty = true;
+    return GRB_OK;
+}
+
+int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_id) {
+    if (!ctx || !d || !out_id) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (d->nv <= 0 || d->nf < 0 || d->nvn < 0 || !d->vertices || (d->nf > 0 && (!d->vidx || !d->fnormals)))
+        return fail(ctx, GRB_ERR_INVALID, "mesh needs vertices, face normals and vertex indices");
+    // the reference would panic on an out-of-range index (renderer.go:318-320, 328-330)
+    for (int64_t i = 0; i < (int64_t)d->nf * 3; i++)
+        if (d->vidx[i] < 0 || d->vidx[i] >= d->nv) return fail(ctx, GRB_ERR_INVALID, "vertex index out of range");
+    if (d->nvn > 0) {
+        if (!d->vnormals || !d->nidx) return fail(ctx, GRB_ERR_INVALID, "mesh with vertex normals needs normal indices");
+        for (int64_t i = 0; i < (int64_t)d->nf * 3; i++)
+            if (d->nidx[i] < 0 || d->nidx[i] >= d->nvn)
+                return fail(ctx, GRB_ERR_INVALID, "normal index out of range (the reference panics: renderer.go:328-330)");
+    }
+    if (int32_t r = set_device(ctx)) return r;
+    MeshHost m;
+    m.live = true;
+    m.dev.nv = d->nv; m.dev.nvn = d->nvn; m.dev.nf = d->nf;
+    std::memcpy(m.bbox, d->bbox, sizeof(m.bbox));
+    int32_t r;
+    float4 *f4;
+    int32_t *i32;
+    float2 *f2;
+    if ((r = upload(ctx, reinterpret_cast<const float4 *>(d->vertices), d->nv, &f4, m.allocs))) goto bad;
+    m.dev.verts = f4;
+    if ((r = upload(ctx, reinterpret_cast<const float4 *>(d->vnormals), d->nvn, &f4, m.allocs))) goto bad;
+    m.dev.vnormals = f4;
+    if ((r = upload(ctx, reinterpret_cast<const float4 *>(d->fnormals), d->nf, &f4, m.allocs))) goto bad;
+    m.dev.fnormals = f4;
+    if ((r = upload(ctx, d->vidx, (size_t)d->nf * 3, &i32, m.allocs))) goto bad;
+    m.dev.vidx = i32;
+    if ((r = upload(ctx, d->nvn > 0 ? d->nidx : nullptr, (size_t)d->nf * 3, &i32, m.allocs))) goto bad;
+    m.dev.nidx = i32;
+    if ((r = upload(ctx, reinterpret_cast<const float2 *>(d->uvs), (size_t)d->nf * 3, &f2, m.allocs))) goto bad;
+    m.dev.uvs = f2;
+    if ((r = upload(ctx, d->tex, d->nf, &i32, m.allocs))) goto bad;
+    m.dev.tex = i32;
+    ctx->meshes.push_back(std::move(m));
+    ctx->meshesDirty = true;
+    ctx->planValid = false;
+    *out_id = (int32_t)ctx->meshes.size() - 1;
+    return GRB_OK;
+bad:
+    for (void *p : m.allocs) cudaFree(p);
+    return r;
+}
+
+int32_t grb_mesh_free(grb_context *ctx, int32_t id) {
+    if (!ctx || id < 0 || id >= (int32_t)ctx->meshes.size() || !ctx->meshes[id].live)
+        return fail(ctx, GRB_ERR_INVALID, "bad mesh id");
+    if (int32_t r = set_device(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (void *p : ctx->meshes[id].allocs) cudaFree(p);
+    ctx->meshes[id] = MeshHost{};
+    ctx->meshesDirty = true;
+    ctx->planValid = false;
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_create(grb_context *ctx, int32_t width, int32_t height, int32_t frames, grb_framebuffer **out) {
+    if (!ctx || !out) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || frames <= 0) return fail(ctx, GRB_ERR_INVALID, "bad framebuffer size");
+    if (int32_t r = set_device(ctx)) return r;
+    grb_framebuffer *fb = new grb_framebuffer{ctx, width, height, frames, nullptr, nullptr, true};
+    const size_t px = (size_t)width * height * frames;
+    cudaError_t e = cudaMalloc((void **)&fb->color, px * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&fb->depth, px * 4);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (fb->color) cudaFree(fb->color);
+        delete fb;
+        return fail(ctx, GRB_ERR_OOM, std::string("framebuffer allocation: ") + cudaGetErrorString(e));
+    }
+    *out = fb;
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_wrap(grb_context *ctx, int32_t width, int32_t height, int32_t frames, void *device_color,
+                             void *device_depth, grb_framebuffer **out) {
+    if (!ctx || !out || !device_color || !device_depth) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || frames <= 0) return fail(ctx, GRB_ERR_INVALID, "bad framebuffer size");
+    if (((uintptr_t)device_color & 15) || ((uintptr_t)device_depth & 15))
+        return fail(ctx, GRB_ERR_INVALID, "wrapped framebuffer memory must be 16-byte aligned");
+    *out = new grb_framebuffer{ctx, width, height, frames, static_cast<uchar4 *>(device_color),
+                               static_cast<float *>(device_depth), false};
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_destroy(grb_framebuffer *fb) {
+    if (!fb) return GRB_OK;
+    if (fb->owned) {
+        cudaSetDevice(fb->ctx->device);
+        cudaStreamSynchronize(fb->ctx->stream);
+        cudaFree(fb->color);
+        cudaFree(fb->depth);
+    }
+    delete fb;
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_device_ptrs(const grb_framebuffer *fb, void **color, void **depth) {
+    if (!fb) return GRB_ERR_INVALID;
+    if (color) *color = fb->color;
+    if (depth) *depth = fb->depth;
+    return GRB_OK;
+}
+
+int32_t grb_draw_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                       const grb_object *objects, int32_t nobj, const grb_draw_params *params) {
+    return draw_impl(ctx, fb, frame0, nframes, objects, nobj, params);
+}
+
+int32_t grb_frame_stats_read(grb_context *ctx, int32_t nframes, grb_frame_stats *stats) {
+    if (!ctx || !stats || nframes <= 0 || nframes > ctx->lastFrames)
+        return fail(ctx, GRB_ERR_INVALID, "no such frames in the last draw");
+    if (int32_t r = set_device(ctx)) return r;
+    std::vector<FrameCounters> c(nframes);
+    CK(ctx, cudaMemcpyAsync(c.data(), ctx->counters.p, nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int32_t f = 0; f < nframes; f++) {
+        stats[f].tpf = (int64_t)c[f].tpf;
+        stats[f].triangles = (int32_t)c[f].triCount;
+        stats[f].big_triangles = (int32_t)c[f].bigCount;
+        stats[f].out_of_domain = (int32_t)c[f].outOfDomain;
+        stats[f].reserved = 0;
+    }
+    return GRB_OK;
+}
+
+int32_t grb_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, const grb_object *objects,
+                 int32_t nobj, const grb_draw_params *params, grb_frame_stats *stats) {
+    if (int32_t r = draw_impl(ctx, fb, frame0, nframes, objects, nobj, params)) return r;
+    if (stats) return grb_frame_stats_read(ctx, nframes, stats);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int32_t grb_read_frames_async(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                              uint8_t *pixels, float *zbuffer) {
+    if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (nframes <= 0 || frame0 < 0 || frame0 + nframes > fb->frames)
+        return fail(ctx, GRB_ERR_INVALID, "frame range outside the framebuffer");
+    if (int32_t r = set_device(ctx)) return r;
+    const size_t px = (size_t)fb->width * fb->height;
+    if (pixels)
+        CK(ctx, cudaMemcpyAsync(pixels, fb->color + frame0 * px, nframes * px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (zbuffer)
+        CK(ctx, cudaMemcpyAsync(zbuffer, fb->depth + frame0 * px, nframes * px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return GRB_OK;
+}
+
+int32_t grb_read_frames(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes, uint8_t *pixels,
+                        float *zbuffer) {
+    if (int32_t r = grb_read_frames_async(ctx, fb, frame0, nframes, pixels, zbuffer)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int32_t grb_matrix_multiply_vec4_batch_device(grb_context *ctx, const float m[16], void *device_vecs, int64_t n) {
+    if (!ctx || !m || (n > 0 && !device_vecs) || n < 0) return fail(ctx, GRB_ERR_INVALID, "bad argument");
+    if (int32_t r = set_device(ctx)) return r;
+    launch_matvec_batch(m, static_cast<float4 *>(device_vecs), n, ctx->stream);
+    if (n > 0) ctx->totalLaunches++;
+    CK(ctx, cudaGetLastError());
+    return GRB_OK;
+}
+
+int32_t grb_matrix_multiply_vec4_batch(grb_context *ctx, const float m[16], float *vecs, int64_t n) {
+    if (!ctx || !m || (n > 0 && !vecs) || n < 0) return fail(ctx, GRB_ERR_INVALID, "bad argument");
+    if (n == 0) return GRB_OK;  // asm_amd64.s:15-17: empty slice is a no-op
+    if (int32_t r = set_device(ctx)) return r;
+    if (int32_t r = ensure(ctx, ctx->seam, (size_t)n, false)) return r;
+    CK(ctx, cudaMemcpyAsync(ctx->seam.p, vecs, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (int32_t r = grb_matrix_multiply_vec4_batch_device(ctx, m, ctx->seam.p, n)) return r;
+    CK(ctx, cudaMemcpyAsync(vecs, ctx->seam.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int32_t grb_debug_read_transformed(grb_context *ctx, int32_t frame, float *out, int64_t capacity_vec4, int64_t *out_n) {
+    if (!ctx || frame < 0 || frame >= ctx->lastFrames) return fail(ctx, GRB_ERR_INVALID, "no such frame in the last draw");
+    if (int32_t r = set_device(ctx)) return r;
+    const int64_t n = ctx->totalVerts;
+    if (out_n) *out_n = n;
+    if (!out) return GRB_OK;
+    if (capacity_vec4 < n) return fail(ctx, GRB_ERR_INVALID, "output too small");
+    if (n) CK(ctx, cudaMemcpyAsync(out, ctx->tv.p + (size_t)frame * n, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_rec *out, float *out_uvs,
+                                 int64_t capacity, int64_t *out_n) {
+    if (!ctx || frame < 0 || frame >= ctx->lastFrames) return fail(ctx, GRB_ERR_INVALID, "no such frame in the last draw");
+    if (int32_t r = set_device(ctx)) return r;
+    FrameCounters c;
+    CK(ctx, cudaMemcpyAsync(&c, ctx->counters.p + frame, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t n = c.triCount;
+    if (out_n) *out_n = n;
+    if (!out) return GRB_OK;
+    if (capacity < n) return fail(ctx, GRB_ERR_INVALID, "output too small");
+    if (n == 0) return GRB_OK;
+    std::vector<grb_triangle_rec> recs(n);
+    std::vector<TriUV> uvs(n);
+    CK(ctx, cudaMemcpy(recs.data(), ctx->rec.p + (size_t)frame * ctx->recCap, n * sizeof(TriRec), cudaMemcpyDeviceToHost));
+    CK(ctx, cudaMemcpy(uvs.data(), ctx->uv.p + (size_t)frame * ctx->recCap, n * sizeof(TriUV), cudaMemcpyDeviceToHost));
+    // slots are block-ordered, blocks land in atomic order: present in submission order
+    std::vector<int64_t> order(n);
+    for (int64_t i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return recs[x].seq1 < recs[y].seq1; });
+    for (int64_t i = 0; i < n; i++) {
+        out[i] = recs[order[i]];
+        if (out_uvs) {
+            if (recs[order[i]].tex >= 0) std::memcpy(out_uvs + 6 * i, &uvs[order[i]], 24);
+            else std::memset(out_uvs + 6 * i, 0, 24);
+        }
+    }
+    return GRB_OK;
+}
+
+int32_t grb_debug_read_visibility(grb_context *ctx, int32_t frame, int32_t *out, int32_t capacity) {
+    if (!ctx || !out || frame < 0 || frame >= ctx->lastFrames) return fail(ctx, GRB_ERR_INVALID, "no such frame in the last draw");
+    const int32_t n = std::min(capacity, ctx->lastNobj);
+    for (int32_t i = 0; i < n; i++) out[i] = ctx->lastVisibility[(size_t)frame * ctx->lastNobj + i];
+    return GRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// gr_types.cuh — device-side data layout shared by the kernels and capi.cu.
+//
+// HBM layout.  Scene data is uploaded once (MeshDev,
+// TexDev).  Everything a draw produces lives in a per-context workspace,
+// struct-of-arrays over the frames of a batch:
+//
+//   tv        [frames][totalVerts]        float4   clip-space vertices        (K1 -> K2)
+//   rec       [frames][recCap]            TriRec   emitted triangles, 64 B    (K2 -> K4,K5)
+//   uv        [frames][recCap]            TriUV    24 B, textured faces only  (K2 -> K5)
+//   blockBase [frames][nFaceBlocks]       u32      first rec slot of a block  (K2 -> K5)
+//   tileCount [frames][nTiles]            u32      (K2 -> K3; K3 re-zeroes)
+//   tileOff   [frames][nTiles+1]          u32      (K3 -> K4,K5)
+//   cursor    [frames][nTiles]            u32      (K3 zeroes -> K4)
+//   binList   [frames][kMaxBinsPerTri*recCap] u32  rec slots per tile         (K4 -> K5)
+//   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles
+//   counters  [frames]                    FrameCounters
+#pragma once
+
+#include <stdint.h>
+
+#include "../../include/gorender_b200.h"
+#include "gr_math.cuh"
+
+namespace gr {
+
+constexpr int kTile = GRB_TILE;            // raster tile edge (pixels)
+constexpr int kTilePix = kTile * kTile;
+constexpr int kFaceBlock = 256;            // faces per setup block
+constexpr int kSeqStride = 2048;           // order keys reserved per face block (>= 7*256)
+constexpr int kMaxFan = 7;                 // clipping.go:10: <= 9 vertices -> <= 7 triangles
+constexpr int kMaxBinsPerTri = 16;         // more tiles than this -> bigList
+constexpr int kCoordLimit = 16383;         // |snapped coord| bound of the int32 edge-function domain
+
+struct MeshDev {
+    const float4 *verts;
+    const float4 *vnormals;
+    const float4 *fnormals;
+    const int32_t *vidx;     // 3 per face
+    const int32_t *nidx;     // 3 per face
+    const float2 *uvs;       // 3 per face
+    const int32_t *tex;      // per face, -1 = nil
+    int32_t nv, nvn, nf, pad;
+};
+
+struct TexDev {
+    const uchar4 *pixels;
+    int32_t type, width, height;
+    float widthF, heightF, scale;
+    uchar4 color;
+    int32_t pad;
+};
+
+// per (frame, object)
+struct FrameObj {
+    float mvp[16];
+    float world[16];
+    int32_t visibility;      // GRB_BOX_*
+    int32_t pad[3];
+};
+
+// per object of the draw list (same for every frame of a batch)
+struct DrawObj {
+    int32_t mesh;
+    int32_t vertBase;        // offset of the object's vertices in tv[frame]
+    int32_t faceBlockBase;   // first face-block (submission order)
+    int32_t vertBlockBase;   // first vertex-block
+};
+
+struct __align__(16) TriRec {   // == grb_triangle_rec, 64 B
+    int32_t x0, y0, x1, y1;
+    int32_t x2, y2;
+    float w0, w1;
+    float w2, i0, i1, i2;
+    int16_t bx0, by0, bx1, by1;
+    int32_t tex;
+    uint32_t seq1;
+};
+static_assert(sizeof(TriRec) == 64, "TriRec must be 64 bytes");
+static_assert(sizeof(grb_triangle_rec) == 64, "ABI record must be 64 bytes");
+
+struct __align__(8) TriUV {
+    float u0, v0, u1, v1, u2, v2;
+};
+
+struct __align__(16) FrameCounters {
+    uint32_t triCount;
+    uint32_t bigCount;
+    uint32_t outOfDomain;
+    uint32_t pad;
+    unsigned long long tpf;
+    unsigned long long pad2;
+};
+
+struct RefTiles {            // the reference's tile grid (renderer.go:50-76)
+    int32_t ntx, nty;        // numTilesX, numTilesY
+    int32_t tw, th;          // tileWidth, tileHeight
+};
+
+struct DrawArgs {
+    // scene
+    const MeshDev *meshes;
+    const TexDev *textures;
+    int32_t ntex;
+    // draw list
+    const DrawObj *objs;
+    const int32_t *vblkObj;     // vertex-block -> object
+    const int32_t *fblkObj;     // face-block   -> object
+    const FrameObj *frameObjs;  // [frames][nobj]
+    int32_t nobj, nVertBlocks, nFaceBlocks, totalVerts;
+    // workspace (per-frame strides in elements)
+    float4 *tv;
+    TriRec *rec;
+    TriUV *uv;
+    uint32_t *blockBase;
+    uint32_t *tileCount;
+    uint32_t *tileOff;
+    uint32_t *cursor;
+    uint32_t *binList;
+    uint32_t *bigList;
+    FrameCounters *counters;
+    uint32_t recCap;
+    // target
+    uchar4 *color;              // [frames][H][W]
+    float *depth;               // [frames][H][W]
+    int32_t width, height;
+    int32_t ntx, nty;           // device tiles
+    int32_t tileRowBegin, tileRowEnd;  // strip, in tile rows
+    // params
+    Mat4 screen;
+    float lx, ly, lz;
+    uint32_t options;
+    float zNear, zFar;
+    RefTiles ref;
+};
+
+}  // namespace gr

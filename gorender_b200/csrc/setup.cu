@@ -1,0 +1,416 @@
+// setup.cu — K1 vertex transform and K2 clip-and-emit / triangle setup.
+//
+// K1 replaces matrixMultiplyVec4Batch on the vertex array
+//    (renderer.go:303-304; asm_amd64.s:22-47): one thread per vertex,
+//    128-bit load, 16 separately rounded FMUL + 12 FADD, 128-bit store.
+// K2 replaces the per-face loop of projectObject (renderer.go:315-396):
+//    gather, backface cull (:246-250), lighting (:326-346), Sutherland–Hodgman
+//    frustum clip (clipping.go:167-236), perspective divide + viewport
+//    (:361-370), integer snap (:182-184), the reference's tile-list membership
+//    rule (:226-244) and TPF, then a block-ordered compaction of the emitted
+//    triangle records plus the device-tile bin counts.
+//
+// One thread per face; a block owns kFaceBlock consecutive faces of one
+// object.  Emitted triangles of a block are written contiguously in
+// submission order (block-level exclusive scan); the block's base slot comes
+// from one atomicAdd, and the submission-order key of a triangle is
+// (faceBlock * kSeqStride + rank in block), which is monotone in
+// (object, face, fan) without any cross-block scan.
+
+#include "gr_types.cuh"
+#include "kernels.h"
+
+namespace gr {
+
+// ---------------------------------------------------------------- K1
+
+__global__ void __launch_bounds__(256) transform_kernel(const __grid_constant__ DrawArgs a) {
+    const int frame = blockIdx.y;
+    const int vb = blockIdx.x;
+    const int o = a.vblkObj[vb];
+    const DrawObj ob = a.objs[o];
+    const FrameObj &fo = a.frameObjs[(size_t)frame * a.nobj + o];
+    if (fo.visibility == GRB_BOX_OUTSIDE) return;  // renderer.go:273-275
+    const MeshDev &m = a.meshes[ob.mesh];
+    const int v = (vb - ob.vertBlockBase) * 256 + threadIdx.x;
+    if (v >= m.nv) return;
+    const float4 p = __ldg(&m.verts[v]);
+    a.tv[(size_t)frame * a.totalVerts + ob.vertBase + v] = mat_vec(fo.mvp, p);
+}
+
+// The build-tag seam itself (asm_amd64.go:8): in place over a device array.
+__global__ void __launch_bounds__(256) matvec_batch_kernel(Mat4 m, float4 *vecs, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        vecs[i] = mat_vec(m.m, vecs[i]);
+}
+
+// ---------------------------------------------------------------- K2 helpers
+
+struct ClipVert {
+    float4 p;
+    float u, v, in;
+};
+
+// clipping.go:93-126
+__device__ __forceinline__ void frustum_plane(int i, float zn, float zf, float4 &P, float4 &N) {
+    switch (i) {
+    case 0: P = make_float4(-1, 0, 0, 1); N = make_float4(1, 0, 0, 1); break;
+    case 1: P = make_float4(1, 0, 0, 1); N = make_float4(-1, 0, 0, 1); break;
+    case 2: P = make_float4(0, -1, 0, 1); N = make_float4(0, 1, 0, 1); break;
+    case 3: P = make_float4(0, 1, 0, 1); N = make_float4(0, -1, 0, 1); break;
+    case 4: P = make_float4(0, 0, zn, 1); N = make_float4(0, 0, -1, 0); break;
+    default: P = make_float4(0, 0, zf, 1); N = make_float4(0, 0, 1, 0); break;
+    }
+}
+
+// clipping.go:74-76
+__device__ __forceinline__ bool plane_inside(float4 P, float4 N, float4 q) { return dot4(sub4(q, P), N) <= 0.0f; }
+
+// clipping.go:79-86 + lerp32 / lerpUV (clipping.go:156-165)
+__device__ __forceinline__ ClipVert plane_intersect(float4 P, float4 N, const ClipVert &A, const ClipVert &B) {
+    const float4 u = sub4(B.p, A.p);
+    const float4 w = sub4(A.p, P);
+    const float d = dot4(N, u);
+    const float n = -dot4(N, w);
+    const float t = fdiv(n, d);
+    ClipVert r;
+    r.p = add4(A.p, mul4(u, t));
+    r.in = fadd(A.in, fmul(fsub(B.in, A.in), t));
+    r.u = fadd(A.u, fmul(fsub(B.u, A.u), t));
+    r.v = fadd(A.v, fmul(fsub(B.v, A.v), t));
+    return r;
+}
+
+// Frustum.ClipTriangle up to the polygon (clipping.go:167-232); returns the
+// vertex count (0 or 3..9) with the polygon left in `poly`.
+__device__ int clip_polygon(ClipVert *poly, ClipVert *tmp, float zn, float zf) {
+    int count = 3;
+    ClipVert *src = poly, *dst = tmp;
+#pragma unroll 1
+    for (int pi = 0; pi < 6; pi++) {
+        float4 P, N;
+        frustum_plane(pi, zn, zf, P, N);
+        int out = 0;
+#pragma unroll 1
+        for (int b = 0; b < count; b++) {
+            const int ai = (b + 1 == count) ? 0 : b + 1;
+            const ClipVert A = src[ai], B = src[b];
+            const bool inA = plane_inside(P, N, A.p);
+            const bool inB = plane_inside(P, N, B.p);
+            // the reference's arrays hold 9 vertices (clipping.go:10) and Go would
+            // panic beyond that; a convex polygon never gets there
+            if (inA) {
+                if (!inB && out < 9) dst[out++] = plane_intersect(P, N, A, B);
+                if (out < 9) dst[out++] = A;
+            } else if (inB) {
+                if (out < 9) dst[out++] = plane_intersect(P, N, A, B);
+            }
+        }
+        if (out == 0) return 0;
+        count = out;
+        ClipVert *t = src; src = dst; dst = t;
+    }
+    if (src != poly)
+        for (int i = 0; i < count; i++) poly[i] = src[i];
+    return count;
+}
+
+struct ScreenVert {
+    float sx, sy, w;
+};
+
+// renderer.go:365-370: p / p.w (4 true divides), full screen-matrix rows, W restored
+__device__ __forceinline__ ScreenVert to_screen(const Mat4 &S, float4 p) {
+    const float4 q = make_float4(fdiv(p.x, p.w), fdiv(p.y, p.w), fdiv(p.z, p.w), fdiv(p.w, p.w));
+    ScreenVert s;
+    s.sx = mat_row(S.m, q);
+    s.sy = mat_row(S.m + 4, q);
+    s.w = p.w;
+    return s;
+}
+
+// `int(a.X)` (renderer.go:182): truncation; outside the int32 edge-function
+// domain (or NaN) the triangle is reported, not rendered.
+__device__ __forceinline__ int snap(float f, bool &bad) {
+    if (!(fabsf(f) < (float)(kCoordLimit + 1))) { bad = true; return 0; }
+    return __float2int_rz(f);
+}
+
+struct Emit {
+    TriRec rec;
+    int tpf;        // number of reference tile lists this triangle is in
+    bool valid;     // gets a record (non-empty raster bbox, ShowFaces)
+    bool bad;       // out of the integer domain
+};
+
+// Everything between the clipper and the rasteriser for one output triangle.
+__device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0, ScreenVert s1, ScreenVert s2,
+                                               float i0, float i1, float i2, int tex) {
+    Emit e;
+    e.valid = false;
+    e.bad = false;
+    e.tpf = 0;
+
+    // identifyTriangleTiles (renderer.go:226-244) on the float screen points
+    const float minX = gomin(gomin(s0.sx, s1.sx), s2.sx), maxX = gomax(gomax(s0.sx, s1.sx), s2.sx);
+    const float minY = gomin(gomin(s0.sy, s1.sy), s2.sy), maxY = gomax(gomax(s0.sy, s1.sy), s2.sy);
+    const float Wf = (float)a.width, Hf = (float)a.height;
+    int c0 = 1 << 30, c1 = -1, r0 = 1 << 30, r1 = -1, nc = 0, nr = 0;
+    for (int c = 0; c < a.ref.ntx; c++) {   // calculateTileBoundaries (renderer.go:50-76)
+        const float sx = (float)(c * a.ref.tw);
+        float ex = fadd(sx, (float)a.ref.tw);
+        if (a.ref.ntx == 1 || ex > Wf) ex = Wf;
+        if (maxX >= sx && minX <= ex) { nc++; c0 = min(c0, c); c1 = max(c1, c); }
+    }
+    for (int r = 0; r < a.ref.nty; r++) {
+        const float sy = (float)(r * a.ref.th);
+        float ey = fadd(sy, (float)a.ref.th);
+        if (a.ref.nty == 1 || ey > Hf) ey = Hf;
+        if (maxY >= sy && minY <= ey) { nr++; r0 = min(r0, r); r1 = max(r1, r); }
+    }
+    e.tpf = nc * nr;
+    if (e.tpf == 0 || !(a.options & GRB_OPT_SHOW_FACES)) return e;
+
+    bool bad = false;
+    TriRec &t = e.rec;
+    t.x0 = snap(s0.sx, bad); t.y0 = snap(s0.sy, bad);
+    t.x1 = snap(s1.sx, bad); t.y1 = snap(s1.sy, bad);
+    t.x2 = snap(s2.sx, bad); t.y2 = snap(s2.sy, bad);
+    if (bad) { e.bad = true; return e; }
+    t.w0 = s0.w; t.w1 = s1.w; t.w2 = s2.w;
+    t.i0 = i0; t.i1 = i1; t.i2 = i2;
+    t.tex = tex;
+    t.seq1 = 0;
+
+    // Pixel (x,y) is finally owned by the highest-index reference tile that
+    // contains it: column min(x / tw, ntx-1).  A triangle is drawn there iff it
+    // is in that tile's list, i.e. iff the column and row pass the float test
+    // above.  Passing columns/rows are contiguous.
+    const int xlo = c0 * a.ref.tw, xhi = (c1 == a.ref.ntx - 1) ? a.width - 1 : (c1 + 1) * a.ref.tw - 1;
+    const int ylo = r0 * a.ref.th, yhi = (r1 == a.ref.nty - 1) ? a.height - 1 : (r1 + 1) * a.ref.th - 1;
+    // rasterizer.go:99-104 (union over the tiles the triangle is listed in)
+    int bx0 = max(max(min(min(t.x0, t.x1), t.x2), xlo), 0);
+    int bx1 = min(min(max(max(t.x0, t.x1), t.x2), xhi), a.width - 1);
+    int by0 = max(max(min(min(t.y0, t.y1), t.y2), ylo), 0);
+    int by1 = min(min(max(max(t.y0, t.y1), t.y2), yhi), a.height - 1);
+    // sort-first strip: keep only this rank's rows
+    by0 = max(by0, a.tileRowBegin * kTile);
+    by1 = min(by1, a.tileRowEnd * kTile - 1);
+    if (bx0 > bx1 || by0 > by1) return e;
+    t.bx0 = (int16_t)bx0; t.by0 = (int16_t)by0; t.bx1 = (int16_t)bx1; t.by1 = (int16_t)by1;
+    e.valid = true;
+    return e;
+}
+
+// Writes the record and counts it into the device tile bins.
+__device__ __forceinline__ void commit_triangle(const DrawArgs &a, int frame, TriRec rec, const TriUV *uv,
+                                                uint32_t slot, uint32_t seq1) {
+    rec.seq1 = seq1;
+    TriRec *dst = a.rec + (size_t)frame * a.recCap + slot;
+    const int4 *s = reinterpret_cast<const int4 *>(&rec);
+    int4 *d = reinterpret_cast<int4 *>(dst);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+    if (rec.tex >= 0) a.uv[(size_t)frame * a.recCap + slot] = *uv;
+
+    const int tx0 = rec.bx0 / kTile, tx1 = rec.bx1 / kTile;
+    const int ty0 = rec.by0 / kTile, ty1 = rec.by1 / kTile;
+    const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+    if (n > kMaxBinsPerTri) {
+        const uint32_t pos = atomicAdd(&a.counters[frame].bigCount, 1u);
+        a.bigList[(size_t)frame * a.recCap + pos] = slot;
+    } else {
+        uint32_t *cnt = a.tileCount + (size_t)frame * a.ntx * a.nty;
+        for (int ty = ty0; ty <= ty1; ty++)
+            for (int tx = tx0; tx <= tx1; tx++) atomicAdd(&cnt[ty * a.ntx + tx], 1u);
+    }
+}
+
+// renderer.go:328-337: xyz(normalize4(world * n)) . L, with w (=1, translated)
+// taking part in the length
+__device__ __forceinline__ float light_intensity(const float *world, float4 n, float lx, float ly, float lz) {
+    const float4 wn = mat_vec(world, n);
+    const float len = fsqrt(fadd(fadd(fadd(fmul(wn.x, wn.x), fmul(wn.y, wn.y)), fmul(wn.z, wn.z)), fmul(wn.w, wn.w)));
+    const float nx = fdiv(wn.x, len), ny = fdiv(wn.y, len), nz = fdiv(wn.z, len);
+    return fadd(0.5f, fmul(dot3(nx, ny, nz, lx, ly, lz), 0.5f));
+}
+
+// Exclusive scan of one int per thread over a 256-thread block; returns the
+// thread's offset and the block total.
+__device__ __forceinline__ int block_exclusive_scan(int v, int &total) {
+    __shared__ int warpSum[kFaceBlock / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warpSum[wid] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kFaceBlock / 32; w++) {
+        const int s = warpSum[w];
+        if (w < wid) base += s;
+        tot += s;
+    }
+    total = tot;
+    return base + inc - v;
+}
+
+// ---------------------------------------------------------------- K2
+
+template <bool CLIP>
+__global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant__ DrawArgs a) {
+    const int frame = blockIdx.y;
+    const int fb = blockIdx.x;
+    const int o = a.fblkObj[fb];
+    const DrawObj ob = a.objs[o];
+    const FrameObj &fo = a.frameObjs[(size_t)frame * a.nobj + o];
+    const int vis = fo.visibility;
+    if (vis == GRB_BOX_OUTSIDE) return;
+    // renderer.go:349: the clipper runs iff FrustumClipping && bbox not fully inside
+    const bool objClips = (a.options & GRB_OPT_FRUSTUM_CLIPPING) && vis != GRB_BOX_INSIDE;
+    if (objClips != CLIP) return;  // the other instantiation owns this block
+
+    const MeshDev &m = a.meshes[ob.mesh];
+    const int f = (fb - ob.faceBlockBase) * kFaceBlock + threadIdx.x;
+
+    bool alive = f < m.nf;
+    float4 v0, v1, v2;
+    float in0 = 0.5f, in1 = 0.5f, in2 = 0.5f;  // ambientStrength (renderer.go:342-346)
+    int tex = -1;
+
+    if (alive) {
+        const float4 *tv = a.tv + (size_t)frame * a.totalVerts + ob.vertBase;
+        const int i0 = __ldg(&m.vidx[3 * f]), i1 = __ldg(&m.vidx[3 * f + 1]), i2 = __ldg(&m.vidx[3 * f + 2]);
+        v0 = tv[i0]; v1 = tv[i1]; v2 = tv[i2];
+        if (a.options & GRB_OPT_BACKFACE_CULLING) {
+            // facingCamera (renderer.go:246-250) on clip-space xyz
+            const float e1x = fsub(v1.x, v0.x), e1y = fsub(v1.y, v0.y), e1z = fsub(v1.z, v0.z);
+            const float e2x = fsub(v2.x, v0.x), e2y = fsub(v2.y, v0.y), e2z = fsub(v2.z, v0.z);
+            const float nx = fsub(fmul(e1y, e2z), fmul(e1z, e2y));
+            const float ny = fsub(fmul(e1z, e2x), fmul(e1x, e2z));
+            const float nz = fsub(fmul(e1x, e2y), fmul(e1y, e2x));
+            const float d = dot3(nx, ny, nz, fsub(0.0f, v0.x), fsub(0.0f, v0.y), fsub(0.0f, v0.z));
+            alive = d > 0.0f;
+        }
+    }
+
+    if (alive) {
+        if (a.options & GRB_OPT_LIGHTING) {
+            if (m.nvn != 0 && !(a.options & GRB_OPT_FLAT_SHADING)) {
+                const int n0 = __ldg(&m.nidx[3 * f]), n1 = __ldg(&m.nidx[3 * f + 1]), n2 = __ldg(&m.nidx[3 * f + 2]);
+                in0 = light_intensity(fo.world, __ldg(&m.vnormals[n0]), a.lx, a.ly, a.lz);
+                in1 = light_intensity(fo.world, __ldg(&m.vnormals[n1]), a.lx, a.ly, a.lz);
+                in2 = light_intensity(fo.world, __ldg(&m.vnormals[n2]), a.lx, a.ly, a.lz);
+            } else {
+                in0 = in1 = in2 = light_intensity(fo.world, __ldg(&m.fnormals[f]), a.lx, a.ly, a.lz);
+            }
+        }
+        // drawProjection (renderer.go:176-178): ShowTextures off => nil texture
+        if ((a.options & GRB_OPT_SHOW_TEXTURES) && m.tex != nullptr) tex = __ldg(&m.tex[f]);
+        if (tex >= a.ntex) tex = -1;
+    }
+
+    TriUV fuv = {0, 0, 0, 0, 0, 0};
+    if (alive && m.uvs != nullptr) {
+        const float2 a0 = __ldg(&m.uvs[3 * f]), a1 = __ldg(&m.uvs[3 * f + 1]), a2 = __ldg(&m.uvs[3 * f + 2]);
+        fuv = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
+    }
+
+    int tpf = 0, nbad = 0;
+    const uint32_t seqBase = (uint32_t)fb * kSeqStride + 1u;
+
+    if constexpr (!CLIP) {
+        Emit e;
+        e.valid = false;
+        if (alive) {
+            e = setup_triangle(a, to_screen(a.screen, v0), to_screen(a.screen, v1), to_screen(a.screen, v2), in0, in1,
+                               in2, tex);
+            tpf = e.tpf;
+            nbad = e.bad ? 1 : 0;
+        }
+        int total;
+        const int off = block_exclusive_scan(e.valid ? 1 : 0, total);
+        __shared__ uint32_t sBase;
+        if (threadIdx.x == 0) {
+            sBase = total ? atomicAdd(&a.counters[frame].triCount, (uint32_t)total) : 0u;
+            a.blockBase[(size_t)frame * a.nFaceBlocks + fb] = sBase;
+        }
+        __syncthreads();
+        if (e.valid) commit_triangle(a, frame, e.rec, &fuv, sBase + off, seqBase + off);
+    } else {
+        ClipVert poly[9], tmp[9];
+        ScreenVert sv[9];
+        int count = 0;
+        unsigned validMask = 0;
+        if (alive) {
+            poly[0] = {v0, fuv.u0, fuv.v0, in0};
+            poly[1] = {v1, fuv.u1, fuv.v1, in1};
+            poly[2] = {v2, fuv.u2, fuv.v2, in2};
+            count = clip_polygon(poly, tmp, a.zNear, a.zFar);
+            if (count < 3) count = 0;  // Triangulate (clipping.go:47-49)
+            for (int i = 0; i < count; i++) sv[i] = to_screen(a.screen, poly[i].p);
+            // fan (0, i+1, i+2)  (clipping.go:54-59)
+            for (int i = 0; i + 2 < count; i++) {
+                const Emit e = setup_triangle(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in,
+                                              poly[i + 2].in, tex);
+                tpf += e.tpf;
+                nbad += e.bad ? 1 : 0;
+                if (e.valid) validMask |= 1u << i;
+            }
+        }
+        int total;
+        int off = block_exclusive_scan(__popc(validMask), total);
+        __shared__ uint32_t sBase;
+        if (threadIdx.x == 0) {
+            sBase = total ? atomicAdd(&a.counters[frame].triCount, (uint32_t)total) : 0u;
+            a.blockBase[(size_t)frame * a.nFaceBlocks + fb] = sBase;
+        }
+        __syncthreads();
+        for (int i = 0; i + 2 < count; i++) {
+            if (!(validMask & (1u << i))) continue;
+            const Emit e = setup_triangle(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in, poly[i + 2].in,
+                                          tex);
+            const TriUV uv = {poly[0].u, poly[0].v, poly[i + 1].u, poly[i + 1].v, poly[i + 2].u, poly[i + 2].v};
+            commit_triangle(a, frame, e.rec, &uv, sBase + off, seqBase + off);
+            off++;
+        }
+    }
+
+    // TPF (renderer.go:436-441) and diagnostics: one atomic per warp
+    for (int d = 16; d > 0; d >>= 1) {
+        tpf += __shfl_xor_sync(0xffffffffu, tpf, d);
+        nbad += __shfl_xor_sync(0xffffffffu, nbad, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (tpf) atomicAdd(&a.counters[frame].tpf, (unsigned long long)tpf);
+        if (nbad) atomicAdd(&a.counters[frame].outOfDomain, (uint32_t)nbad);
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+
+void launch_transform(const DrawArgs &a, int nframes, cudaStream_t s) {
+    if (a.nVertBlocks == 0) return;
+    transform_kernel<<<dim3(a.nVertBlocks, nframes), 256, 0, s>>>(a);
+}
+
+void launch_setup(const DrawArgs &a, int nframes, bool anyPlain, bool anyClip, cudaStream_t s) {
+    if (a.nFaceBlocks == 0) return;
+    if (anyPlain) setup_kernel<false><<<dim3(a.nFaceBlocks, nframes), kFaceBlock, 0, s>>>(a);
+    if (anyClip) setup_kernel<true><<<dim3(a.nFaceBlocks, nframes), kFaceBlock, 0, s>>>(a);
+}
+
+void launch_matvec_batch(const float m[16], float4 *vecs, long long n, cudaStream_t s) {
+    if (n <= 0) return;
+    Mat4 mm;
+    for (int i = 0; i < 16; i++) mm.m[i] = m[i];
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    matvec_batch_kernel<<<(unsigned)blocks, 256, 0, s>>>(mm, vecs, n);
+}
+
+}  // namespace gr

@@ -1,0 +1,377 @@
+"""Frame pipeline — host-side mirror of the reference's `renderer.go` /
+`rasterizer.go` public API, with the body of `Draw` running on the GPU through
+the C ABI (include/gorender_b200.h).
+
+Kept from the reference: `Camera` (renderer.go:22-26), `FrameBuffer` with
+`Width/Height/ZBuffer/Pixels/Pixels2/SwapBuffers` (rasterizer.go:7-34),
+`Renderer` with its option fields and `TPF` (renderer.go:83-101), `NewRenderer`
+(renderer.go:114-164) and `Draw(objects, camera)` (renderer.go:443-483: no
+return value; results are side effects on `fb.Pixels`, `fb.ZBuffer`, `r.TPF`;
+failure is an exception, the analogue of the Go shim's panic).
+
+Added for the B200: `DrawBatch` (frame-parallel pose batches)
+and `rows=(begin, end)` (sort-first strips).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _cabi
+from . import vecmath as vm
+from .mesh import Mesh, Object
+from .texture import Texture, TextureTypeSolidColor
+
+
+class Camera:
+    """renderer.go:22-26."""
+
+    def __init__(self, Position=(0, 0, 0), Direction=(0, 0, -1), Up=(0, 1, 0)):
+        self.Position = np.asarray(Position, dtype=np.float32)
+        self.Direction = np.asarray(Direction, dtype=np.float32)
+        self.Up = np.asarray(Up, dtype=np.float32)
+
+
+class Device:
+    """One grb_context (one GPU).  Owns uploaded meshes / textures."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = _cabi.load()
+        h = C.c_void_p()
+        rc = self.lib.grb_context_create(int(device), C.byref(h))
+        if rc != 0:
+            raise _cabi.GorenderError(rc, self.lib.grb_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+        self._meshes = {}    # id(Mesh) -> (mesh id, Mesh kept alive, texture ids tuple)
+        self._textures = {}  # id(Texture) -> (texture id, Texture kept alive, scale)
+        if stream is not None:
+            self.set_stream(stream)
+
+    def check(self, rc: int) -> None:
+        _cabi.check(self.h, rc)
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        self.check(self.lib.grb_context_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self) -> None:
+        self.check(self.lib.grb_context_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.grb_launch_count(self.h))
+
+    def set_kernel_timing(self, enable: bool) -> None:
+        self.check(self.lib.grb_context_set_kernel_timing(self.h, int(bool(enable))))
+
+    def kernel_times(self):
+        ms = (C.c_double * 5)()
+        n = C.c_int64()
+        self.check(self.lib.grb_kernel_times(self.h, ms, C.byref(n)))
+        names = ("transform", "setup", "bin_scan", "bin_fill", "raster")
+        return dict(zip(names, [float(x) for x in ms])), int(n.value)
+
+    # -- assets
+    def texture_id(self, t: Optional[Texture]) -> int:
+        if t is None:
+            return -1
+        ent = self._textures.get(id(t))
+        if ent is not None:
+            if ent[2] != float(t.scale):  # Texture.SetScale after upload
+                self.check(self.lib.grb_texture_set_scale(self.h, ent[0], float(t.scale)))
+                self._textures[id(t)] = (ent[0], t, float(t.scale))
+            return ent[0]
+        out = C.c_int32(-1)
+        color = (C.c_uint8 * 4)(*t.color)
+        if t.typ == TextureTypeSolidColor:
+            rc = self.lib.grb_texture_upload(self.h, t.typ, 0, 0, float(t.scale), color, None, C.byref(out))
+        else:
+            px = np.ascontiguousarray(t.pixels, dtype=np.uint8)
+            rc = self.lib.grb_texture_upload(self.h, t.typ, t.width, t.height, float(t.scale), color,
+                                             C.c_void_p(px.ctypes.data), C.byref(out))
+        self.check(rc)
+        self._textures[id(t)] = (out.value, t, float(t.scale))
+        return out.value
+
+    def mesh_id(self, m: Mesh) -> int:
+        F = m.Faces
+        tex_ids = tuple(self.texture_id(t) for t in F.Textures)
+        ent = self._meshes.get(id(m))
+        if ent is not None and ent[2] == tex_ids and ent[3] is F.TextureIndex:
+            return ent[0]
+        d = _cabi.grb_mesh_desc()
+        nf = len(F)
+        verts = np.ascontiguousarray(m.Vertices, dtype=np.float32)
+        vns = np.ascontiguousarray(m.VertexNormals, dtype=np.float32)
+        fns = np.ascontiguousarray(m.FaceNormals, dtype=np.float32)
+        vidx = np.ascontiguousarray(F.VertexIndices, dtype=np.int32)
+        nidx = np.ascontiguousarray(F.NormalIndices, dtype=np.int32)
+        uvs = np.ascontiguousarray(F.UVs, dtype=np.float32)
+        lut = np.array(list(tex_ids) + [-1], dtype=np.int32)  # index -1 -> nil
+        tex = np.ascontiguousarray(lut[F.TextureIndex], dtype=np.int32)
+        d.nv, d.nvn, d.nf = len(verts), len(vns), nf
+        d.vertices = _cabi.ptr(verts, C.c_float)
+        d.vnormals = _cabi.ptr(vns, C.c_float) if len(vns) else None
+        d.fnormals = _cabi.ptr(fns, C.c_float) if nf else None
+        d.vidx = _cabi.ptr(vidx, C.c_int32) if nf else None
+        d.nidx = _cabi.ptr(nidx, C.c_int32) if (nf and len(vns)) else None
+        d.uvs = _cabi.ptr(uvs, C.c_float) if nf else None
+        d.tex = _cabi.ptr(tex, C.c_int32) if nf else None
+        bbox = np.ascontiguousarray(m.BoundingBox, dtype=np.float32).reshape(32)
+        d.bbox = (C.c_float * 32)(*bbox.tolist())
+        out = C.c_int32(-1)
+        self.check(self.lib.grb_mesh_upload(self.h, C.byref(d), C.byref(out)))
+        if ent is not None:
+            self.check(self.lib.grb_mesh_free(self.h, ent[0]))
+        self._meshes[id(m)] = (out.value, m, tex_ids, F.TextureIndex)
+        return out.value
+
+    def matrixMultiplyVec4Batch(self, m: np.ndarray, vecs: np.ndarray) -> None:
+        """The reference's build-tag seam (asm_amd64.go:8 / asm_purego.go:9): in place."""
+        m = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+        assert vecs.dtype == np.float32 and vecs.flags["C_CONTIGUOUS"] and vecs.size % 4 == 0
+        self.check(self.lib.grb_matrix_multiply_vec4_batch(
+            self.h, _cabi.ptr(m, C.c_float), C.c_void_p(vecs.ctypes.data), vecs.size // 4))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.grb_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_devices = {}
+
+
+def default_device(device: int = 0) -> Device:
+    d = _default_devices.get(device)
+    if d is None:
+        d = _default_devices[device] = Device(device)
+    return d
+
+
+class FrameBuffer:
+    """rasterizer.go:7-23.  `Pixels`, `Pixels2` are (H, W, 4) uint8 RGBA,
+    `ZBuffer` is (H, W) float32 — host arrays, as in the reference; the device
+    copy (`frames` of them for batches) lives behind `handle`."""
+
+    def __init__(self, width: int, height: int, frames: int = 1, device: Optional[Device] = None,
+                 device_color: Optional[int] = None, device_depth: Optional[int] = None):
+        self.Width = int(width)
+        self.Height = int(height)
+        self.Frames = int(frames)
+        self.Pixels = np.zeros((height, width, 4), dtype=np.uint8)
+        self.Pixels2 = np.zeros((height, width, 4), dtype=np.uint8)
+        self.ZBuffer = np.zeros((height, width), dtype=np.float32)
+        self.dev = device or default_device()
+        h = C.c_void_p()
+        if device_color is not None:
+            rc = self.dev.lib.grb_framebuffer_wrap(self.dev.h, width, height, frames, C.c_void_p(device_color),
+                                                   C.c_void_p(device_depth), C.byref(h))
+        else:
+            rc = self.dev.lib.grb_framebuffer_create(self.dev.h, width, height, frames, C.byref(h))
+        self.dev.check(rc)
+        self.handle = h
+
+    def SwapBuffers(self) -> None:
+        """rasterizer.go:32-34."""
+        self.Pixels, self.Pixels2 = self.Pixels2, self.Pixels
+
+    def device_ptrs(self) -> Tuple[int, int]:
+        c, d = C.c_void_p(), C.c_void_p()
+        self.dev.check(self.dev.lib.grb_framebuffer_device_ptrs(self.handle, C.byref(c), C.byref(d)))
+        return int(c.value), int(d.value)
+
+    def read(self, frame0: int = 0, nframes: int = 1, pixels: Optional[np.ndarray] = None,
+             zbuffer: Optional[np.ndarray] = None, want_z: bool = True):
+        """Copy device frames to host arrays (allocated if not given)."""
+        if pixels is None:
+            pixels = np.empty((nframes, self.Height, self.Width, 4), dtype=np.uint8)
+        if zbuffer is None and want_z:
+            zbuffer = np.empty((nframes, self.Height, self.Width), dtype=np.float32)
+        self.dev.check(self.dev.lib.grb_read_frames(
+            self.dev.h, self.handle, frame0, nframes, C.c_void_p(pixels.ctypes.data),
+            C.c_void_p(zbuffer.ctypes.data) if zbuffer is not None else None))
+        return pixels, zbuffer
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.dev.lib.grb_framebuffer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def NewFrameBuffer(width: int, height: int, frames: int = 1, device: Optional[Device] = None) -> FrameBuffer:
+    """rasterizer.go:15-23."""
+    return FrameBuffer(width, height, frames, device)
+
+
+class Renderer:
+    """renderer.go:83-112 (public fields) and :114-164 (NewRenderer)."""
+
+    def __init__(self, fb: FrameBuffer, parallel: bool = True):
+        self.fb = fb
+        self.dev = fb.dev
+        # renderer.go:115-122
+        self.aspectX = np.float32(np.float32(fb.Width) / np.float32(fb.Height))
+        self.aspectY = np.float32(np.float32(fb.Height) / np.float32(fb.Width))
+        self.fovY = np.float32(45 * (math.pi / 180))
+        self.fovX = np.float32(2 * math.atan(math.tan(float(self.fovY / np.float32(2))) * float(self.aspectX)))
+        self.zNear, self.zFar = np.float32(0.0), np.float32(50.0)
+        # renderer.go:130-137
+        self.FrustumClipping = True
+        self.ShowVertices = False
+        self.ShowEdges = False
+        self.ShowFaces = True
+        self.BackfaceCulling = True
+        self.Lighting = True
+        self.FlatShading = False
+        self.ShowTextures = True
+        self.TPF = 0
+        self.DebugEnabled = False
+        self.DebugInfo: list = []
+        # renderer.go:144,151: numTiles is 1 when !parallel, else max(NumCPU, 16) (16 on any
+        # host the reference runs on: more than 16 CPUs panic)
+        self.numTiles = 16 if parallel else 1
+        self.last_stats = None
+
+    # -- options -> ABI bitmask
+    def options(self) -> int:
+        o = 0
+        if self.FrustumClipping: o |= _cabi.GRB_OPT_FRUSTUM_CLIPPING
+        if self.ShowFaces: o |= _cabi.GRB_OPT_SHOW_FACES
+        if self.BackfaceCulling: o |= _cabi.GRB_OPT_BACKFACE_CULLING
+        if self.Lighting: o |= _cabi.GRB_OPT_LIGHTING
+        if self.FlatShading: o |= _cabi.GRB_OPT_FLAT_SHADING
+        if self.ShowTextures: o |= _cabi.GRB_OPT_SHOW_TEXTURES
+        return o
+
+    def draw_params(self, rows: Optional[Tuple[int, int]] = None) -> _cabi.grb_draw_params:
+        p = _cabi.grb_draw_params()
+        screen = vm.NewScreenMatrix(self.fb.Width, self.fb.Height)          # renderer.go:264
+        light = vm.light_direction()                                        # renderer.go:265
+        p.screen = (C.c_float * 16)(*screen.reshape(16).tolist())
+        p.light = (C.c_float * 3)(*light.tolist())
+        p.options = self.options()
+        p.z_near, p.z_far = float(self.zNear), float(self.zFar)
+        p.ref_tiles = self.numTiles
+        p.row_begin, p.row_end = (rows if rows is not None else (0, 0))
+        return p
+
+    def perspective(self) -> np.ndarray:
+        return vm.NewPerspectiveMatrix(self.fovY, self.aspectX, self.zNear, self.zFar)  # renderer.go:257
+
+    def object_matrices(self, obj: Object, camera: Camera, perspective=None, view=None):
+        """renderer.go:255-262."""
+        world = vm.NewWorldMatrix(obj.Scale, obj.Rotation, obj.Translation)
+        if view is None:
+            view = vm.NewViewMatrix(camera.Position, camera.Direction, camera.Up)
+        if perspective is None:
+            perspective = self.perspective()
+        return world, vm.mvp_matrix(perspective, view, world)
+
+    def pack_objects(self, objects: Sequence[Object], cameras: Sequence[Camera],
+                     rotations_y: Optional[np.ndarray] = None) -> np.ndarray:
+        """grb_object array [len(cameras)][len(objects)].  `rotations_y[f]`, when
+        given, overrides every object's Rotation.Y in frame f (the demo spin,
+        main.go:229-233) without touching the objects."""
+        nobj = len(objects)
+        mesh_ids = [self.dev.mesh_id(o.Mesh) for o in objects]
+        arr = np.zeros((len(cameras), max(nobj, 0)), dtype=_cabi.OBJECT_DTYPE)
+        persp = self.perspective()
+        for f, cam in enumerate(cameras):
+            view = vm.NewViewMatrix(cam.Position, cam.Direction, cam.Up)
+            for i, o in enumerate(objects):
+                if rotations_y is not None:
+                    rot = np.array([o.Rotation[0], rotations_y[f], o.Rotation[2]], dtype=np.float32)
+                    world = vm.NewWorldMatrix(o.Scale, rot, o.Translation)
+                    mvp = vm.mvp_matrix(persp, view, world)
+                else:
+                    world, mvp = self.object_matrices(o, cam, persp, view)
+                arr[f, i]["mesh"] = mesh_ids[i]
+                arr[f, i]["world"] = world.reshape(16)
+                arr[f, i]["mvp"] = mvp.reshape(16)
+        return arr
+
+    # -- the hot path
+    def draw_packed(self, packed: np.ndarray, frame0: int = 0, rows=None, sync: bool = True):
+        """Issue one batched draw of packed[frames][nobj] into fb frames [frame0, ...)."""
+        nframes, nobj = packed.shape
+        p = self.draw_params(rows)
+        lib = self.dev.lib
+        if sync:
+            stats = np.zeros(nframes, dtype=_cabi.STATS_DTYPE)
+            self.dev.check(lib.grb_draw(self.dev.h, self.fb.handle, frame0, nframes,
+                                        C.c_void_p(packed.ctypes.data), nobj, C.byref(p),
+                                        C.c_void_p(stats.ctypes.data)))
+            self.last_stats = stats
+            return stats
+        self.dev.check(lib.grb_draw_async(self.dev.h, self.fb.handle, frame0, nframes,
+                                          C.c_void_p(packed.ctypes.data), nobj, C.byref(p)))
+        return None
+
+    def Draw(self, objects: Sequence[Object], camera: Camera, read_z: bool = True) -> None:
+        """renderer.go:443-483.  Side effects: fb.Pixels, fb.ZBuffer, self.TPF."""
+        packed = self.pack_objects(objects, [camera])
+        stats = self.draw_packed(packed, 0)
+        self.TPF = int(stats["tpf"][0])
+        fb = self.fb
+        fb.read(0, 1, fb.Pixels.reshape(1, fb.Height, fb.Width, 4),
+                fb.ZBuffer.reshape(1, fb.Height, fb.Width) if read_z else None, want_z=read_z)
+
+    def DrawBatch(self, objects: Sequence[Object], cameras: Sequence[Camera],
+                  rotations_y: Optional[np.ndarray] = None, read_back: bool = True, read_z: bool = True):
+        """Frame-parallel batch: frame f = Draw(objects, cameras[f]).  The
+        framebuffer must have at least len(cameras) frames.  Returns (pixels,
+        zbuffer, tpf) host arrays when read_back."""
+        if len(cameras) > self.fb.Frames:
+            raise ValueError("framebuffer has fewer frames than the batch")
+        packed = self.pack_objects(objects, cameras, rotations_y)
+        stats = self.draw_packed(packed, 0)
+        self.TPF = int(stats["tpf"][-1])
+        if not read_back:
+            return None, None, stats["tpf"].copy()
+        px, z = self.fb.read(0, len(cameras), want_z=read_z)
+        return px, z, stats["tpf"].copy()
+
+    # -- stage read-backs (parity tests)
+    def debug_transformed(self, frame: int = 0) -> np.ndarray:
+        n = C.c_int64()
+        lib = self.dev.lib
+        self.dev.check(lib.grb_debug_read_transformed(self.dev.h, frame, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        self.dev.check(lib.grb_debug_read_transformed(self.dev.h, frame, C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
+        return out
+
+    def debug_triangles(self, frame: int = 0):
+        n = C.c_int64()
+        lib = self.dev.lib
+        self.dev.check(lib.grb_debug_read_triangles(self.dev.h, frame, None, None, 0, C.byref(n)))
+        recs = np.zeros(n.value, dtype=_cabi.TRIANGLE_DTYPE)
+        uvs = np.zeros((n.value, 6), dtype=np.float32)
+        if n.value:
+            self.dev.check(lib.grb_debug_read_triangles(self.dev.h, frame, C.c_void_p(recs.ctypes.data),
+                                                        C.c_void_p(uvs.ctypes.data), n.value, C.byref(n)))
+        return recs, uvs
+
+    def debug_visibility(self, frame: int, nobj: int) -> np.ndarray:
+        out = np.zeros(nobj, dtype=np.int32)
+        self.dev.check(self.dev.lib.grb_debug_read_visibility(self.dev.h, frame, C.c_void_p(out.ctypes.data), nobj))
+        return out
+
+
+def NewRenderer(fb: FrameBuffer, parallel: bool = True) -> Renderer:
+    """renderer.go:114-164."""
+    return Renderer(fb, parallel)

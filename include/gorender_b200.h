@@ -1,0 +1,215 @@
+/*
+ * gorender_b200.h — C ABI of the B200-native gorender hot path.
+ *
+ * The reference (maxpoletaev/gorender) has no plugin / FFI layer: everything
+ * is `package main`.  The boundary this library sits behind is therefore the
+ * reference's Go API for the per-frame path — `NewFrameBuffer`
+ * (rasterizer.go:15), `NewRenderer` (renderer.go:114), `(*Renderer).Draw`
+ * (renderer.go:443), plus its one build-tag seam `matrixMultiplyVec4Batch`
+ * (asm_amd64.go:8 / asm_purego.go:9).  Each entry point below names the
+ * reference interface it replaces.  INTEGRATION.md shows the cgo binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all matrices are row-major float[16]
+ *     (reference `Matrix [4][4]float32`, matrix.go:3); vectors are xyzw
+ *     float[4] (`Vec4`, vector.go:87-89); colours are RGBA8 (`color.RGBA`);
+ *   - every call returns GRB_OK (0) or an error code; `grb_last_error`
+ *     returns the message.  The reference's `Draw` cannot fail
+ *     (renderer.go:443), so a Go shim turns non-zero into panic;
+ *   - entries may be called from any OS thread (each sets its device), one
+ *     in-flight call per context;
+ *   - host pointers are only read/written during the call; nothing
+ *     caller-owned is retained (cgo pointer rules);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     fails with GRB_ERR_CUDA.
+ */
+#ifndef GORENDER_B200_H
+#define GORENDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRB_ABI_VERSION 1
+
+enum {
+    GRB_OK = 0,
+    GRB_ERR_INVALID = 1,   /* bad argument / handle / index            */
+    GRB_ERR_CUDA = 2,      /* CUDA runtime error (message has details) */
+    GRB_ERR_OOM = 3,       /* device or pinned-host allocation failed  */
+    GRB_ERR_STATE = 4      /* call not valid in the current state      */
+};
+
+/* Renderer option bits == the reference's Renderer bool fields
+ * (renderer.go:90-97; defaults renderer.go:130-137). */
+enum {
+    GRB_OPT_FRUSTUM_CLIPPING = 1u << 0,
+    GRB_OPT_SHOW_FACES       = 1u << 1,
+    GRB_OPT_BACKFACE_CULLING = 1u << 2,
+    GRB_OPT_LIGHTING         = 1u << 3,
+    GRB_OPT_FLAT_SHADING     = 1u << 4,
+    GRB_OPT_SHOW_TEXTURES    = 1u << 5,
+    GRB_OPT_DEFAULT = GRB_OPT_FRUSTUM_CLIPPING | GRB_OPT_SHOW_FACES |
+                      GRB_OPT_BACKFACE_CULLING | GRB_OPT_LIGHTING |
+                      GRB_OPT_SHOW_TEXTURES
+};
+
+/* TextureType (texture.go:11-15). */
+enum { GRB_TEX_SOLID = 0, GRB_TEX_IMAGE = 1, GRB_TEX_IMAGE_FAST = 2 };
+
+/* BoxVisibility (clipping.go:23-27). */
+enum { GRB_BOX_OUTSIDE = 0, GRB_BOX_INTERSECT = 1, GRB_BOX_INSIDE = 2 };
+
+typedef struct grb_context grb_context;
+typedef struct grb_framebuffer grb_framebuffer;
+
+/* Flattened `Mesh` (mesh.go:19-26) + `[]Face` (mesh.go:12-17): a Go `Face`
+ * holds a Go pointer and 64-bit ints and cannot cross cgo, so the shim
+ * flattens it once at upload. */
+typedef struct grb_mesh_desc {
+    int32_t nv, nvn, nf;
+    const float *vertices;   /* nv  * 4  Mesh.Vertices      (x,y,z,1)            */
+    const float *vnormals;   /* nvn * 4  Mesh.VertexNormals (x,y,z,1), may be NULL */
+    const float *fnormals;   /* nf  * 4  Mesh.FaceNormals   (x,y,z,1)            */
+    const int32_t *vidx;     /* nf * 3   Face.VertexIndices                      */
+    const int32_t *nidx;     /* nf * 3   Face.NormalIndices (NULL if nvn == 0)   */
+    const float *uvs;        /* nf * 6   Face.UVs (u0,v0,u1,v1,u2,v2), may be NULL */
+    const int32_t *tex;      /* nf       texture id per face, -1 = nil; may be NULL */
+    float bbox[32];          /* Mesh.BoundingBox: 8 corners * xyzw (mesh.go:41-50) */
+} grb_mesh_desc;
+
+/* One object of one frame: mesh handle + the finished matrices the unchanged
+ * host code computes (renderer.go:255-262), so the host libm never has to be
+ * matched on the device. */
+typedef struct grb_object {
+    int32_t mesh;
+    float world[16];         /* NewWorldMatrix(Scale, Rotation, Translation) */
+    float mvp[16];           /* ((I * perspective) * view) * world           */
+} grb_object;
+
+typedef struct grb_draw_params {
+    float screen[16];        /* NewScreenMatrix(width, height)  (renderer.go:264) */
+    float light[3];          /* normalize(-1, 1, 1)             (renderer.go:265) */
+    uint32_t options;        /* GRB_OPT_*                                         */
+    float z_near, z_far;     /* frustum planes (renderer.go:121-122: 0, 50)       */
+    int32_t ref_tiles;       /* the reference's numTiles: 16 (parallel) or 1; decides
+                                TPF and the tile-list membership rule (renderer.go:226-244) */
+    int32_t row_begin;       /* sort-first strip: rasterise rows [row_begin,row_end); */
+    int32_t row_end;         /*   both multiples of GRB_TILE; 0,0 = whole frame       */
+} grb_draw_params;
+
+#define GRB_TILE 32          /* device raster tile edge, pixels */
+
+/* Device record of one emitted screen-space triangle (the reference's
+ * `Triangle`, renderer.go:29-34, after the integer snap of renderer.go:182-184). */
+typedef struct grb_triangle_rec {
+    int32_t x0, y0, x1, y1, x2, y2;   /* int(a.X), int(a.Y) ...            */
+    float w0, w1, w2;                 /* clip-space w (the rasteriser's z) */
+    float i0, i1, i2;                 /* vertex intensities                */
+    int16_t bx0, by0, bx1, by1;       /* inclusive raster bbox after the tile-list rule */
+    int32_t tex;                      /* texture id, -1 = face colour      */
+    uint32_t seq1;                    /* submission-order key + 1          */
+} grb_triangle_rec;
+
+/* Per-frame statistics. */
+typedef struct grb_frame_stats {
+    int64_t tpf;             /* Renderer.TPF (renderer.go:436-441)                  */
+    int32_t triangles;       /* emitted triangles that reached the rasteriser       */
+    int32_t big_triangles;   /* of those, handled by the whole-tile cooperative path */
+    int32_t out_of_domain;   /* triangles dropped: snapped |coord| > 16383 or NaN   */
+    int32_t reserved;
+} grb_frame_stats;
+
+/* ---- context ------------------------------------------------------------ */
+
+int32_t grb_abi_version(void);
+/* Message of the last failing call on `ctx` (or of the last failing
+ * grb_context_create when ctx == NULL).  Never NULL. */
+const char *grb_last_error(const grb_context *ctx);
+
+int32_t grb_context_create(int32_t device, grb_context **out);
+int32_t grb_context_destroy(grb_context *ctx);
+/* Run all work of `ctx` on this cudaStream_t (NULL = the context's own stream). */
+int32_t grb_context_set_stream(grb_context *ctx, void *cuda_stream);
+int32_t grb_context_synchronize(grb_context *ctx);
+/* When enabled, every draw records CUDA events between its kernels and
+ * accumulates per-kernel time (ms) retrievable with grb_kernel_times. */
+int32_t grb_context_set_kernel_timing(grb_context *ctx, int32_t enable);
+/* out_ms[0..4] = transform, setup, bin-scan, bin-fill, raster; out_launches =
+ * number of kernel launches accumulated.  Resets the accumulators. */
+int32_t grb_kernel_times(grb_context *ctx, double out_ms[5], int64_t *out_launches);
+/* Total kernel launches issued by this context since creation. */
+int64_t grb_launch_count(const grb_context *ctx);
+
+/* Pinned host memory for read-back targets (cudaHostAlloc). */
+void *grb_host_alloc(uint64_t bytes);
+void grb_host_free(void *p);
+
+/* ---- assets (replaces nothing on the hot path: one-time upload of what
+ *      LoadObjFile / NewImageTexture produced; texture.go:19-63, mesh.go:53-69) */
+
+int32_t grb_texture_upload(grb_context *ctx, int32_t type, int32_t width, int32_t height,
+                           float scale, const uint8_t color[4], const uint8_t *pixels,
+                           int32_t *out_id);
+/* Texture.SetScale (texture.go:65-67). */
+int32_t grb_texture_set_scale(grb_context *ctx, int32_t id, float scale);
+int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *desc, int32_t *out_id);
+int32_t grb_mesh_free(grb_context *ctx, int32_t id);
+
+/* ---- framebuffer: NewFrameBuffer (rasterizer.go:15-23) ------------------
+ * `frames` device frames of RGBA8 colour + f32 depth each (frames > 1 for
+ * frame-parallel batches).  Clear + DotGrid (rasterizer.go:36-52) are
+ * generated inside the raster kernel; there is no separate clear pass. */
+int32_t grb_framebuffer_create(grb_context *ctx, int32_t width, int32_t height, int32_t frames,
+                               grb_framebuffer **out);
+/* Same, over caller-owned device memory (e.g. torch tensors): colour
+ * frames*H*W*4 bytes, depth frames*H*W floats. */
+int32_t grb_framebuffer_wrap(grb_context *ctx, int32_t width, int32_t height, int32_t frames,
+                             void *device_color, void *device_depth, grb_framebuffer **out);
+int32_t grb_framebuffer_destroy(grb_framebuffer *fb);
+int32_t grb_framebuffer_device_ptrs(const grb_framebuffer *fb, void **color, void **depth);
+
+/* ---- the hot path: (*Renderer).Draw (renderer.go:443-483) ----------------
+ * Renders `nframes` frames into fb frames [frame0, frame0+nframes).  Every
+ * frame draws the same `nobj` meshes; objects[f*nobj + i] carries frame f's
+ * matrices for object i (frame-parallel pose batches: SURVEY.md §8e).
+ * Asynchronous on the context stream. */
+int32_t grb_draw_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                       const grb_object *objects, int32_t nobj, const grb_draw_params *params);
+/* Synchronous single-call form: draw, wait, return per-frame stats
+ * (stats may be NULL; else nframes entries). */
+int32_t grb_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                 const grb_object *objects, int32_t nobj, const grb_draw_params *params,
+                 grb_frame_stats *stats);
+/* Stats of the frames of the most recent draw (synchronises). */
+int32_t grb_frame_stats_read(grb_context *ctx, int32_t nframes, grb_frame_stats *stats);
+
+/* FrameBuffer.Pixels / FrameBuffer.ZBuffer (rasterizer.go:7-13): copy frames
+ * [frame0, frame0+nframes) to host.  Either pointer may be NULL.  The async
+ * form needs pinned memory (grb_host_alloc) to overlap with rendering. */
+int32_t grb_read_frames(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                        uint8_t *pixels, float *zbuffer);
+int32_t grb_read_frames_async(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                              uint8_t *pixels, float *zbuffer);
+
+/* ---- the build-tag seam: matrixMultiplyVec4Batch (asm_amd64.go:8-11,
+ *      asm_amd64.s:7-50, asm_purego.go:9-19).  In place on n host Vec4s. */
+int32_t grb_matrix_multiply_vec4_batch(grb_context *ctx, const float m[16], float *vecs, int64_t n);
+/* Same on device memory already resident in HBM (n Vec4s), async. */
+int32_t grb_matrix_multiply_vec4_batch_device(grb_context *ctx, const float m[16], void *device_vecs, int64_t n);
+
+/* ---- stage read-backs for parity tests (Object.TransformedVertices,
+ *      mesh.go:76; the emitted `Triangle`s, renderer.go:372-377) ---------- */
+int32_t grb_debug_read_transformed(grb_context *ctx, int32_t frame, float *out, int64_t capacity_vec4,
+                                   int64_t *out_n);
+int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_rec *out, float *out_uvs /* 6 per tri, may be NULL */,
+                                 int64_t capacity, int64_t *out_n);
+/* BoxVisibility (clipping.go:131-154) of each object of `frame` in the last draw. */
+int32_t grb_debug_read_visibility(grb_context *ctx, int32_t frame, int32_t *out, int32_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
