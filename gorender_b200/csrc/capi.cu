@@ -51,11 +51,15 @@ struct grb_framebuffer {
     uchar4 *color;
     float *depth;
     bool owned;
+    // read-backs run on the context's copy stream so that the D2H of one
+    // framebuffer overlaps the rendering of another
+    cudaEvent_t drawDone = nullptr, readDone = nullptr;
+    bool pendingRead = false;
 };
 
 struct grb_context {
     int device = 0;
-    cudaStream_t ownStream = nullptr, stream = nullptr;
+    cudaStream_t ownStream = nullptr, stream = nullptr, copyStream = nullptr;
     mutable std::string err;
 
     std::vector<MeshHost> meshes;
@@ -399,6 +403,10 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
 
     const bool anyVisible = anyPlain || anyClip;
     cudaStream_t s = ctx->stream;
+    if (fb->pendingRead) {  // do not overwrite frames a read-back is still copying
+        CK(ctx, cudaStreamWaitEvent(s, fb->readDone, 0));
+        fb->pendingRead = false;
+    }
     const bool tm = ctx->timing;
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[0], s));
     if (anyVisible) launch_transform(a, nframes, s);
@@ -412,6 +420,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     launch_raster(a, nframes, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[5], s));
     CK(ctx, cudaGetLastError());
+    CK(ctx, cudaEventRecord(fb->drawDone, s));
 
     int launches = 2;  // scan + raster
     if (anyVisible) launches += 2 + (anyPlain ? 1 : 0) + (anyClip ? 1 : 0);
@@ -461,6 +470,11 @@ int32_t grb_context_create(int32_t device, grb_context **out) {
         return fail(nullptr, GRB_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
     }
     ctx->stream = ctx->ownStream;
+    if ((e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->ownStream);
+        delete ctx;
+        return fail(nullptr, GRB_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
+    }
     for (int i = 0; i < kStagingRing; i++) cudaEventCreateWithFlags(&ctx->stagingDone[i], cudaEventDisableTiming);
     for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->tev[i]);
     *out = ctx;
@@ -471,6 +485,7 @@ int32_t grb_context_destroy(grb_context *ctx) {
     if (!ctx) return GRB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copyStream);
     for (auto &m : ctx->meshes)
         for (void *p : m.allocs) cudaFree(p);
     for (auto &t : ctx->textures)
@@ -487,6 +502,7 @@ int32_t grb_context_destroy(grb_context *ctx) {
     for (int i = 0; i < 6; i++)
         if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     delete ctx;
     return GRB_OK;
 }
@@ -503,6 +519,7 @@ int32_t grb_context_synchronize(grb_context *ctx) {
     if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
     if (int32_t r = set_device(ctx)) return r;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->copyStream));
     return GRB_OK;
 }
 
@@ -646,6 +663,8 @@ int32_t grb_framebuffer_create(grb_context *ctx, int32_t width, int32_t height, 
         delete fb;
         return fail(ctx, GRB_ERR_OOM, std::string("framebuffer allocation: ") + cudaGetErrorString(e));
     }
+    cudaEventCreateWithFlags(&fb->drawDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&fb->readDone, cudaEventDisableTiming);
     *out = fb;
     return GRB_OK;
 }
@@ -657,19 +676,26 @@ int32_t grb_framebuffer_wrap(grb_context *ctx, int32_t width, int32_t height, in
     if (width <= 0 || height <= 0 || frames <= 0) return fail(ctx, GRB_ERR_INVALID, "bad framebuffer size");
     if (((uintptr_t)device_color & 15) || ((uintptr_t)device_depth & 15))
         return fail(ctx, GRB_ERR_INVALID, "wrapped framebuffer memory must be 16-byte aligned");
-    *out = new grb_framebuffer{ctx, width, height, frames, static_cast<uchar4 *>(device_color),
-                               static_cast<float *>(device_depth), false};
+    if (int32_t r = set_device(ctx)) return r;
+    grb_framebuffer *fb = new grb_framebuffer{ctx, width, height, frames, static_cast<uchar4 *>(device_color),
+                                              static_cast<float *>(device_depth), false};
+    cudaEventCreateWithFlags(&fb->drawDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&fb->readDone, cudaEventDisableTiming);
+    *out = fb;
     return GRB_OK;
 }
 
 int32_t grb_framebuffer_destroy(grb_framebuffer *fb) {
     if (!fb) return GRB_OK;
+    cudaSetDevice(fb->ctx->device);
+    cudaStreamSynchronize(fb->ctx->stream);
+    cudaStreamSynchronize(fb->ctx->copyStream);
     if (fb->owned) {
-        cudaSetDevice(fb->ctx->device);
-        cudaStreamSynchronize(fb->ctx->stream);
         cudaFree(fb->color);
         cudaFree(fb->depth);
     }
+    if (fb->drawDone) cudaEventDestroy(fb->drawDone);
+    if (fb->readDone) cudaEventDestroy(fb->readDone);
     delete fb;
     return GRB_OK;
 }
@@ -712,24 +738,31 @@ int32_t grb_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t 
     return GRB_OK;
 }
 
-int32_t grb_read_frames_async(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+int32_t grb_read_frames_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
                               uint8_t *pixels, float *zbuffer) {
     if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
     if (nframes <= 0 || frame0 < 0 || frame0 + nframes > fb->frames)
         return fail(ctx, GRB_ERR_INVALID, "frame range outside the framebuffer");
     if (int32_t r = set_device(ctx)) return r;
     const size_t px = (size_t)fb->width * fb->height;
-    if (pixels)
-        CK(ctx, cudaMemcpyAsync(pixels, fb->color + frame0 * px, nframes * px * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (zbuffer)
-        CK(ctx, cudaMemcpyAsync(zbuffer, fb->depth + frame0 * px, nframes * px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaStream_t cs = ctx->copyStream;
+    // everything queued on the render stream so far (draws, or the caller's own work on a
+    // wrapped framebuffer) completes before the copy starts
+    CK(ctx, cudaEventRecord(fb->drawDone, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(cs, fb->drawDone, 0));
+    if (pixels) CK(ctx, cudaMemcpyAsync(pixels, fb->color + frame0 * px, nframes * px * 4, cudaMemcpyDeviceToHost, cs));
+    if (zbuffer) CK(ctx, cudaMemcpyAsync(zbuffer, fb->depth + frame0 * px, nframes * px * 4, cudaMemcpyDeviceToHost, cs));
+    CK(ctx, cudaEventRecord(fb->readDone, cs));
+    fb->pendingRead = true;
     return GRB_OK;
 }
 
-int32_t grb_read_frames(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes, uint8_t *pixels,
+int32_t grb_read_frames(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, uint8_t *pixels,
                         float *zbuffer) {
     if (int32_t r = grb_read_frames_async(ctx, fb, frame0, nframes, pixels, zbuffer)) return r;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->copyStream));
+    fb->pendingRead = false;
     return GRB_OK;
 }
 

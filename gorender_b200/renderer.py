@@ -128,6 +128,20 @@ class Device:
         self._meshes[id(m)] = (out.value, m, tex_ids, F.TextureIndex)
         return out.value
 
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """numpy array over cudaHostAlloc'ed memory (freed when the array is collected)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = self.lib.grb_host_alloc(max(nbytes, 1))
+        if not p:
+            raise MemoryError(f"grb_host_alloc({nbytes}) failed")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        import weakref
+
+        weakref.finalize(buf, self.lib.grb_host_free, C.c_void_p(p))
+        return arr
+
     def matrixMultiplyVec4Batch(self, m: np.ndarray, vecs: np.ndarray) -> None:
         """The reference's build-tag seam (asm_amd64.go:8 / asm_purego.go:9): in place."""
         m = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
@@ -200,6 +214,14 @@ class FrameBuffer:
             self.dev.h, self.handle, frame0, nframes, C.c_void_p(pixels.ctypes.data),
             C.c_void_p(zbuffer.ctypes.data) if zbuffer is not None else None))
         return pixels, zbuffer
+
+    def read_async(self, frame0: int, nframes: int, pixels: Optional[np.ndarray], zbuffer: Optional[np.ndarray]) -> None:
+        """Queue the copy on the context's copy stream (targets should be `Device.pinned_array`s);
+        it overlaps draws into other framebuffers.  `Device.synchronize()` waits for it."""
+        self.dev.check(self.dev.lib.grb_read_frames_async(
+            self.dev.h, self.handle, frame0, nframes,
+            C.c_void_p(pixels.ctypes.data) if pixels is not None else None,
+            C.c_void_p(zbuffer.ctypes.data) if zbuffer is not None else None))
 
     def close(self) -> None:
         if getattr(self, "handle", None):

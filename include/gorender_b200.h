@@ -189,9 +189,13 @@ int32_t grb_frame_stats_read(grb_context *ctx, int32_t nframes, grb_frame_stats 
 /* FrameBuffer.Pixels / FrameBuffer.ZBuffer (rasterizer.go:7-13): copy frames
  * [frame0, frame0+nframes) to host.  Either pointer may be NULL.  The async
  * form needs pinned memory (grb_host_alloc) to overlap with rendering. */
-int32_t grb_read_frames(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+int32_t grb_read_frames(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
                         uint8_t *pixels, float *zbuffer);
-int32_t grb_read_frames_async(grb_context *ctx, const grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+/* Copies run on the context's own copy stream, ordered after everything
+ * queued so far on the render stream; a later draw into the same framebuffer
+ * waits for them.  With two framebuffers, the read-back of one overlaps the
+ * rendering of the other.  grb_context_synchronize waits for both streams. */
+int32_t grb_read_frames_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
                               uint8_t *pixels, float *zbuffer);
 
 /* ---- the build-tag seam: matrixMultiplyVec4Batch (asm_amd64.go:8-11,

@@ -13,6 +13,7 @@
 #include "gorender_oracle.h"
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
@@ -826,6 +827,20 @@ int32_t orc_renderer_draw(orc_renderer *r, const orc_mesh *meshes, int32_t nmesh
     r->tpf = 0;
     for (unsigned i = 0; i < r->num_tiles; i++) r->tpf += (int64_t)r->tile_tris[i].size();
     return 0;
+}
+
+// Timed CPU baseline: nframes consecutive Draw calls, frame f using
+// objects[f*nobj .. f*nobj+nobj).  Returns wall-clock seconds spent inside the
+// Draw calls (steady clock), or a negative value on bad arguments.
+double orc_renderer_draw_sequence(orc_renderer *r, const orc_mesh *meshes, int32_t nmesh,
+                                  const orc_texture *textures, int32_t ntex,
+                                  const orc_object *objects, int32_t nobj, int32_t nframes,
+                                  const float screen[16], const float light[3], uint32_t options) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int32_t f = 0; f < nframes; f++)
+        if (orc_renderer_draw(r, meshes, nmesh, textures, ntex, objects + (size_t)f * nobj, nobj, screen, light, options))
+            return -1.0;
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 const uint8_t *orc_renderer_pixels(const orc_renderer *r) { return reinterpret_cast<const uint8_t *>(r->fb.pix.data()); }

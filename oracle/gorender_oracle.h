@@ -103,6 +103,15 @@ int32_t orc_renderer_draw(orc_renderer *r,
                           const float screen[16], const float light[3],
                           uint32_t options);
 
+/* Timed CPU baseline: nframes consecutive Draw calls (frame f draws
+ * objects[f*nobj ...]); returns the seconds spent, measured in C. */
+double orc_renderer_draw_sequence(orc_renderer *r,
+                                  const orc_mesh *meshes, int32_t nmesh,
+                                  const orc_texture *textures, int32_t ntex,
+                                  const orc_object *objects, int32_t nobj, int32_t nframes,
+                                  const float screen[16], const float light[3],
+                                  uint32_t options);
+
 const uint8_t *orc_renderer_pixels(const orc_renderer *r);   /* W*H*4 */
 const float *orc_renderer_zbuffer(const orc_renderer *r);    /* W*H   */
 int64_t orc_renderer_tpf(const orc_renderer *r);

@@ -69,6 +69,9 @@ class Oracle:
         L.orc_renderer_draw.restype = C.c_int32
         L.orc_renderer_draw.argtypes = [C.c_void_p, C.POINTER(orc_mesh), C.c_int32, C.POINTER(orc_texture), C.c_int32,
                                         C.POINTER(orc_object), C.c_int32, c_float_p, c_float_p, C.c_uint32]
+        L.orc_renderer_draw_sequence.restype = C.c_double
+        L.orc_renderer_draw_sequence.argtypes = [C.c_void_p, C.POINTER(orc_mesh), C.c_int32, C.POINTER(orc_texture), C.c_int32,
+                                                 C.POINTER(orc_object), C.c_int32, C.c_int32, c_float_p, c_float_p, C.c_uint32]
         L.orc_renderer_pixels.restype = C.c_void_p
         L.orc_renderer_pixels.argtypes = [C.c_void_p]
         L.orc_renderer_zbuffer.restype = C.c_void_p
@@ -184,63 +187,73 @@ class Oracle:
         return tuple(out)
 
     # ---- Renderer.Draw
-    def draw(self, renderer, objects, camera, threads=0, record=False, rotation_y=None, handle=None):
-        """Run the oracle on the same inputs `renderer.Draw(objects, camera)` would get.
-        Returns dict(pixels, zbuffer, tpf, writes, triangles, visibility)."""
+    def marshal(self, renderer, objects, cameras, rotations_y=None):
+        """ctypes arrays for `frames = len(cameras)` consecutive draws of `objects`."""
         import gorender_b200.vecmath as vm
 
         fb = renderer.fb
         keep = []
-        # unique meshes / textures
         meshes, mesh_index, textures, tex_index = [], {}, [], {}
-        objs = (orc_object * max(len(objects), 1))()
+        nobj = len(objects)
+        objs = (orc_object * max(nobj * len(cameras), 1))()
         persp = renderer.perspective()
-        view = vm.NewViewMatrix(camera.Position, camera.Direction, camera.Up)
-        for i, o in enumerate(objects):
+        for o in objects:
             m = o.Mesh
-            if id(m) not in mesh_index:
-                F = m.Faces
-                ids = []
-                for t in F.Textures:
-                    if id(t) not in tex_index:
-                        tex_index[id(t)] = len(textures)
-                        textures.append(self._texture_struct(t, keep))
-                    ids.append(tex_index[id(t)])
-                lut = np.array(ids + [-1], dtype=np.int32)
-                arrs = dict(
-                    v=np.ascontiguousarray(m.Vertices, np.float32), vn=np.ascontiguousarray(m.VertexNormals, np.float32),
-                    fn=np.ascontiguousarray(m.FaceNormals, np.float32), vi=np.ascontiguousarray(F.VertexIndices, np.int32),
-                    ni=np.ascontiguousarray(F.NormalIndices, np.int32), uv=np.ascontiguousarray(F.UVs, np.float32),
-                    tx=np.ascontiguousarray(lut[F.TextureIndex], np.int32))
-                keep.append(arrs)
-                s = orc_mesh()
-                s.nv, s.nvn, s.nf = len(arrs["v"]), len(arrs["vn"]), len(arrs["vi"])
-                s.vertices, s.vnormals, s.fnormals = _fp(arrs["v"]), _fp(arrs["vn"]), _fp(arrs["fn"])
-                s.vidx, s.nidx, s.uvs, s.tex = _ip(arrs["vi"]), _ip(arrs["ni"]), _fp(arrs["uv"]), _ip(arrs["tx"])
-                s.bbox = (C.c_float * 32)(*np.asarray(m.BoundingBox, np.float32).reshape(32).tolist())
-                mesh_index[id(m)] = len(meshes)
-                meshes.append(s)
-            if rotation_y is not None:
-                rot = np.array([o.Rotation[0], rotation_y, o.Rotation[2]], dtype=np.float32)
-                world = vm.NewWorldMatrix(o.Scale, rot, o.Translation)
-                mvp = vm.mvp_matrix(persp, view, world)
-            else:
-                world, mvp = renderer.object_matrices(o, camera, persp, view)
-            objs[i].mesh = mesh_index[id(m)]
-            objs[i].world = (C.c_float * 16)(*world.reshape(16).tolist())
-            objs[i].mvp = (C.c_float * 16)(*mvp.reshape(16).tolist())
+            if id(m) in mesh_index:
+                continue
+            F = m.Faces
+            ids = []
+            for t in F.Textures:
+                if id(t) not in tex_index:
+                    tex_index[id(t)] = len(textures)
+                    textures.append(self._texture_struct(t, keep))
+                ids.append(tex_index[id(t)])
+            lut = np.array(ids + [-1], dtype=np.int32)
+            arrs = dict(
+                v=np.ascontiguousarray(m.Vertices, np.float32), vn=np.ascontiguousarray(m.VertexNormals, np.float32),
+                fn=np.ascontiguousarray(m.FaceNormals, np.float32), vi=np.ascontiguousarray(F.VertexIndices, np.int32),
+                ni=np.ascontiguousarray(F.NormalIndices, np.int32), uv=np.ascontiguousarray(F.UVs, np.float32),
+                tx=np.ascontiguousarray(lut[F.TextureIndex], np.int32))
+            keep.append(arrs)
+            s = orc_mesh()
+            s.nv, s.nvn, s.nf = len(arrs["v"]), len(arrs["vn"]), len(arrs["vi"])
+            s.vertices, s.vnormals, s.fnormals = _fp(arrs["v"]), _fp(arrs["vn"]), _fp(arrs["fn"])
+            s.vidx, s.nidx, s.uvs, s.tex = _ip(arrs["vi"]), _ip(arrs["ni"]), _fp(arrs["uv"]), _ip(arrs["tx"])
+            s.bbox = (C.c_float * 32)(*np.asarray(m.BoundingBox, np.float32).reshape(32).tolist())
+            mesh_index[id(m)] = len(meshes)
+            meshes.append(s)
+        for f, camera in enumerate(cameras):
+            view = vm.NewViewMatrix(camera.Position, camera.Direction, camera.Up)
+            for i, o in enumerate(objects):
+                if rotations_y is not None:
+                    rot = np.array([o.Rotation[0], rotations_y[f], o.Rotation[2]], dtype=np.float32)
+                    world = vm.NewWorldMatrix(o.Scale, rot, o.Translation)
+                    mvp = vm.mvp_matrix(persp, view, world)
+                else:
+                    world, mvp = renderer.object_matrices(o, camera, persp, view)
+                k = f * nobj + i
+                objs[k].mesh = mesh_index[id(o.Mesh)]
+                objs[k].world = (C.c_float * 16)(*world.reshape(16).tolist())
+                objs[k].mvp = (C.c_float * 16)(*mvp.reshape(16).tolist())
         mesh_arr = (orc_mesh * max(len(meshes), 1))(*meshes)
         tex_arr = (orc_texture * max(len(textures), 1))(*textures)
         screen = np.ascontiguousarray(vm.NewScreenMatrix(fb.Width, fb.Height)).reshape(16)
         light = np.ascontiguousarray(vm.light_direction())
+        return dict(keep=keep, meshes=mesh_arr, nmesh=len(meshes), textures=tex_arr, ntex=len(textures), objs=objs,
+                    nobj=nobj, nframes=len(cameras), screen=screen, light=light, options=renderer.options())
 
+    def draw(self, renderer, objects, camera, threads=0, record=False, rotation_y=None, handle=None):
+        """Run the oracle on the same inputs `renderer.Draw(objects, camera)` would get.
+        Returns dict(pixels, zbuffer, tpf, writes, triangles, visibility)."""
+        fb = renderer.fb
+        m = self.marshal(renderer, objects, [camera], None if rotation_y is None else [rotation_y])
         own = handle is None
         r = handle if handle is not None else self.lib.orc_renderer_create(fb.Width, fb.Height, renderer.numTiles, threads)
         assert r
         try:
             self.lib.orc_renderer_record_triangles(r, int(record))
-            rc = self.lib.orc_renderer_draw(r, mesh_arr, len(meshes), tex_arr, len(textures), objs, len(objects),
-                                            _fp(screen), _fp(light), renderer.options())
+            rc = self.lib.orc_renderer_draw(r, m["meshes"], m["nmesh"], m["textures"], m["ntex"], m["objs"], m["nobj"],
+                                            _fp(m["screen"]), _fp(m["light"]), m["options"])
             assert rc == 0
             n = fb.Width * fb.Height
             px = np.ctypeslib.as_array(C.cast(self.lib.orc_renderer_pixels(r), C.POINTER(C.c_uint8)), (n * 4,))
@@ -261,3 +274,21 @@ class Oracle:
             if own:
                 self.lib.orc_renderer_destroy(r)
         return out
+
+    def time_sequence(self, renderer, objects, cameras, rotations_y=None, threads=16, warmup=2):
+        """Seconds (measured in C) for len(cameras) consecutive Draw calls in the reference's
+        threaded structure; the timed CPU baseline of bench.py.  Returns (seconds, frames, tpf)."""
+        fb = renderer.fb
+        m = self.marshal(renderer, objects, cameras, rotations_y)
+        r = self.lib.orc_renderer_create(fb.Width, fb.Height, renderer.numTiles, threads)
+        assert r
+        try:
+            args = (m["meshes"], m["nmesh"], m["textures"], m["ntex"])
+            tail = (_fp(m["screen"]), _fp(m["light"]), m["options"])
+            if warmup:
+                self.lib.orc_renderer_draw_sequence(r, *args, m["objs"], m["nobj"], min(warmup, m["nframes"]), *tail)
+            sec = self.lib.orc_renderer_draw_sequence(r, *args, m["objs"], m["nobj"], m["nframes"], *tail)
+            assert sec >= 0
+            return float(sec), m["nframes"], int(self.lib.orc_renderer_tpf(r))
+        finally:
+            self.lib.orc_renderer_destroy(r)

@@ -1,0 +1,64 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol
+include/gorender_b200.h declares, and refuses to run without a CUDA device
+(no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gorender_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "gorender_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(grb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    names = header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in gorender_b200.h but not exported"
+    assert sorted(_cabi.SIGNATURES) == names, "ctypes signature table out of sync with the header"
+    assert lib.grb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_cabi.grb_object) == 4 + 64 + 64
+    assert C.sizeof(_cabi.grb_triangle_rec) == 64
+    assert C.sizeof(_cabi.grb_frame_stats) == 24
+    assert C.sizeof(_cabi.grb_draw_params) == 64 + 12 + 4 + 8 + 12
+    assert _cabi.grb_mesh_desc.bbox.offset == 72 and C.sizeof(_cabi.grb_mesh_desc) == 72 + 128
+
+
+def test_no_cpu_fallback():
+    """Without a device the library fails loudly instead of computing on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    lib = _cabi.load()
+    h = C.c_void_p()
+    rc = lib.grb_context_create(0, C.byref(h))
+    assert rc == 2 and not h.value
+    assert b"no CUDA device" in lib.grb_last_error(None)
+    import gorender_b200 as g
+
+    with pytest.raises(_cabi.GorenderError):
+        g.Device(0)
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "gorender_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_binding" not in text and "liboracle" not in text and "gorender_oracle" not in text, f

@@ -73,7 +73,11 @@ def test_matrix_multiply_vec4_batch_seam(device, oracle):
         assert np.array_equal(want.view(np.uint32), oracle.matvec4_batch(m, vecs, sse=True).view(np.uint32))
         got = np.ascontiguousarray(vecs.copy())
         device.matrixMultiplyVec4Batch(m, got)
-        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        # NaN payloads differ by architecture (x86 default NaN 0xffc00000, sm_100 0x7fffffff) and
+        # never reach an output (a NaN fails every z-test); everything else is bit-exact
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan])
     one = np.array([[1, 1, 1, 1]], np.float32)
     device.matrixMultiplyVec4Batch(m, one)
     assert one.tolist() == [[np.float32(1.8453332), np.float32(3.159851), np.float32(3.9696174), 1.0]]
