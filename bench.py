@@ -5,9 +5,9 @@ sphere at 1280x720 (BASELINE.json configs[2], "C3"), beside the CPU reference ar
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
 
-A "step" is one batched Draw of `--frames` consecutive frames of the demo spin
-(main.go:229-233: Rotation.Y += 0.01 per frame) of the C3 scene, every frame
-into its own device framebuffer.  N > 1 is frame-parallel: each
+A "step" renders `--frames` consecutive frames of the demo spin (main.go:229-233:
+Rotation.Y += 0.01 per frame) of the C3 scene, issued as batched Draws of `--batch`
+frames, every frame of a batch into its own device framebuffer.  N > 1 is frame-parallel: each
 rank renders its own `--frames` frames per step, no data-path collective, weak
 scaling.  One JSON line is printed by rank 0.
 
@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="frames per step (batched Draw)")
+    ap.add_argument("--frames", type=int, default=1024, help="frames per step")
+    ap.add_argument("--batch", type=int, default=64, help="frames per batched Draw call")
     ap.add_argument("--cpu-sample-frames", type=int, default=400, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -75,7 +76,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -96,9 +97,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, ln in self.lines:
-            if t0 is not None and not (t0 <= ts <= t1 + 0.15):
-                continue
+        lines = self.lines
+        if t0 is not None:
+            inside = [(ts, ln) for ts, ln in lines if t0 <= ts <= t1 + 0.05]
+            # a very short timed region may fall between two samples: take the nearest ones
+            lines = inside or sorted(lines, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:2]
+        for ts, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -148,15 +152,15 @@ def run_reference(args, rank: int):
     threads = max(16, 1)  # numTiles workers (renderer.go:151-155)
     frames = max(1, min(args.frames, 8))  # bounded sample per step
     nfaces = sum(len(o.Mesh.Faces) for o in objs)
-    rot_all = spin_frames(0, (args.warmup + args.steps) * frames)
-    for w in range(args.warmup):
-        orc.time_sequence(r, objs, [cam] * frames, rot_all[w * frames:(w + 1) * frames], threads=threads, warmup=0)
+    nsteps = args.warmup + args.steps
+    timer = orc.sequence_timer(r, objs, [cam] * (nsteps * frames), spin_frames(0, nsteps * frames), threads=threads)
     total = 0.0
     tpf = 0
-    for s in range(args.steps):
-        k = (args.warmup + s) * frames
-        sec, _, tpf = orc.time_sequence(r, objs, [cam] * frames, rot_all[k:k + frames], threads=threads, warmup=0)
-        total += sec
+    for s in range(nsteps):
+        sec, tpf = timer.run(s * frames, frames)
+        if s >= args.warmup:
+            total += sec
+    timer.close()
     fps = args.steps * frames / total
     value = fps * nfaces / 1e6
     sample = f"{frames} consecutive demo-spin frames per step x {args.steps} steps"
@@ -191,23 +195,28 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    F, K, W = args.frames, args.steps, args.warmup
+    B = max(1, min(args.batch, args.frames))
+    F = (args.frames // B) * B            # frames per step, a whole number of batches
+    NB = F // B
+    K, W = args.steps, args.warmup
     objs, cam = build_scene()
     nfaces = sum(len(o.Mesh.Faces) for o in objs)
     nverts = sum(len(o.Mesh.Vertices) for o in objs)
 
     stream = torch.cuda.Stream()
     dev = g.Device(local_rank, stream.cuda_stream)
-    fbs = [g.FrameBuffer(WIDTH, HEIGHT, F, dev) for _ in range(2)]
+    fbs = [g.FrameBuffer(WIDTH, HEIGHT, B, dev) for _ in range(2)]
     rends = [g.Renderer(fb) for fb in fbs]
 
-    # per-step matrices, precomputed on the host like the Go caller would (renderer.go:255-262);
-    # each rank renders its own frames of the spin
-    nsteps_total = W + K
+    # per-frame matrices, computed on the host like the Go caller would (renderer.go:255-262);
+    # each rank renders its own frames of the spin.  A few distinct steps are prepared and cycled.
+    nprep = min(W + K, 3)
     packed = []
-    for s in range(nsteps_total):
+    for s in range(nprep):
         first = (s * world + rank) * F
-        packed.append(np.ascontiguousarray(rends[0].pack_objects(objs, [cam] * F, spin_frames(first, F))))
+        rot = spin_frames(first, F)
+        packed.append([np.ascontiguousarray(rends[0].pack_objects(objs, [cam] * B, rot[b * B:(b + 1) * B]))
+                       for b in range(NB)])
 
     def barrier():
         if dist is not None:
@@ -216,7 +225,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dev.synchronize()
 
     def step_device(s):
-        rends[s & 1].draw_packed(packed[s % nsteps_total], 0, sync=False)
+        for b in range(NB):
+            rends[b & 1].draw_packed(packed[s % nprep][b], 0, sync=False)
 
     # ---- leg 1: device-resident throughput (the `value`)
     with torch.cuda.stream(stream):
@@ -224,6 +234,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             step_device(s)
         barrier()
         sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            time.sleep(0.1)
         launches0 = dev.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -236,20 +248,21 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         ms = e0.elapsed_time(e1)
         launches = dev.launch_count() - launches0
         clocks = sampler.stop(t0, t1) if sampler else None
-    stats = np.zeros(F, dtype=g._cabi.STATS_DTYPE)
-    dev.check(dev.lib.grb_frame_stats_read(dev.h, F, stats.ctypes.data))
+    stats = np.zeros(B, dtype=g._cabi.STATS_DTYPE)
+    dev.check(dev.lib.grb_frame_stats_read(dev.h, B, stats.ctypes.data))
 
     # ---- leg 2: end to end through the C ABI with host buffers
-    host_px = [dev.pinned_array((F, HEIGHT, WIDTH, 4), np.uint8) for _ in range(2)]
-    host_z = [dev.pinned_array((F, HEIGHT, WIDTH), np.float32) for _ in range(2)]
+    host_px = [dev.pinned_array((B, HEIGHT, WIDTH, 4), np.uint8) for _ in range(2)]
+    host_z = [dev.pinned_array((B, HEIGHT, WIDTH), np.float32) for _ in range(2)]
 
     def step_e2e(s):
-        b = s & 1
-        rends[b].draw_packed(packed[s % nsteps_total], 0, sync=False)   # H2D of the matrices happens inside
-        fbs[b].read_async(0, F, host_px[b], host_z[b])
+        for b in range(NB):
+            k = b & 1
+            rends[k].draw_packed(packed[s % nprep][b], 0, sync=False)   # H2D of the matrices happens inside
+            fbs[k].read_async(0, B, host_px[k], host_z[k])           # waits for the draw; overlaps the next one
 
     with torch.cuda.stream(stream):
-        for s in range(W):
+        for s in range(min(W, 2)):
             step_e2e(s)
         barrier()
         t0 = time.perf_counter()
@@ -258,22 +271,21 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dev.synchronize()
         e2e_sec = time.perf_counter() - t0
         barrier()
-    checksum = int(host_px[(W + K - 1) & 1][F - 1].sum())  # the read-back is real
+    checksum = int(host_px[(NB - 1) & 1][B - 1].sum())  # the read-back is real
 
     # ---- leg 3: per-kernel CUDA-event times (roofline of the dominant kernel)
     dev.set_kernel_timing(True)
     with torch.cuda.stream(stream):
-        for s in range(3):
-            step_device(s)
+        step_device(0)
         dev.synchronize()
         dev.kernel_times()
-        nt = 5
+        nt = 2
         for s in range(nt):
             step_device(s)
         dev.synchronize()
     ktimes, _ = dev.kernel_times()
     dev.set_kernel_timing(False)
-    ktimes = {k: v / nt for k, v in ktimes.items()}  # ms per launch (one launch per kernel per step)
+    ktimes = {k: v / (nt * NB) for k, v in ktimes.items()}  # ms per launch (each kernel launches once per batch)
 
     # ---- max over ranks
     if dist is not None:
@@ -298,14 +310,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "raster": 8.0 * WIDTH * HEIGHT + 64.0 * tris + 4.0 * tris,  # colour + depth out, records + list in
     }
     dom = max(ktimes, key=lambda k: ktimes[k])
-    dom_bytes = alg[dom] * F
+    dom_bytes = alg[dom] * B
     achieved = dom_bytes / (ktimes[dom] * 1e-3) / 1e9
     path_bytes = 16.0 * nverts + 12.0 * nfaces + 16.0 * nfaces + 8.0 * WIDTH * HEIGHT
     roofline = {
         "bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": ktimes[dom],
-        "kernel_ms_per_step": ktimes, "kernel_share": {k: v / max(sum(ktimes.values()), 1e-12) for k, v in ktimes.items()},
+        "kernel_ms_per_launch": ktimes, "frames_per_launch": B, "kernel_share": {k: v / max(sum(ktimes.values()), 1e-12) for k, v in ktimes.items()},
         "path_bytes_per_frame": path_bytes, "path_achieved_gbs": path_bytes * fps / world / 1e9,
         "path_frac": path_bytes * fps / world / 1e9 / hbm_peak,
     }
@@ -317,7 +329,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
         orc = Oracle()
         n = args.cpu_sample_frames
-        sec, n, _ = orc.time_sequence(rends[0], objs, [cam] * n, spin_frames(0, n), threads=16, warmup=3)
+        timer = orc.sequence_timer(rends[0], objs, [cam] * n, spin_frames(0, n), threads=16)
+        timer.run(0, min(n, 5))
+        sec, _ = timer.run(0, n)
+        timer.close()
         cpu = {"value": n / sec * nfaces / 1e6, "unit": UNIT, "fps": n / sec, "cores": os.cpu_count(), "threads": 16,
                "kind": "port", "sample": f"{n} consecutive demo-spin frames of the same C3 scene ({sec:.1f} s), oracle "
                "in the reference's threaded structure (1 projection task per object + 16 tile tasks)"}
@@ -331,14 +346,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "config": {
                 "workload": "C3: 200k-triangle geodesic sphere (n=100), 1280x720, flat shading, untextured, "
                             "default camera, demo spin (BASELINE.json configs[2])",
-                "frames_per_step": F, "parallelism": f"frame-parallel x{world}",
-                "l2": f"no flush needed: one step touches {F} x 7.4 MB of framebuffers plus ~{F * 12} MB of "
+                "frames_per_step": F, "frames_per_draw_call": B, "parallelism": f"frame-parallel x{world}",
+                "l2": f"no flush needed: every batched draw writes {B} x 7.4 MB of framebuffers and ~{B * 12} MB of "
                       "intermediates, far more than the 126 MB L2",
                 "published_reference": "README.md:10-13: ~10 Mtps HUD metric / ~100 FPS on an Intel MacBook Pro",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "fps": e2e_fps,
-                    "h2d_bytes_per_step": int(packed[0].nbytes),
-                    "d2h_bytes_per_step": int(host_px[0].nbytes + host_z[0].nbytes), "checksum": checksum},
+                    "h2d_bytes_per_step": int(sum(p.nbytes for p in packed[0])),
+                    "d2h_bytes_per_step": int(NB * (host_px[0].nbytes + host_z[0].nbytes)), "checksum": checksum,
+                    "reads_back": "pixels (RGBA8) and z-buffer (f32) of every frame into pinned host memory"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

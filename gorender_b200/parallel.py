@@ -60,3 +60,33 @@ def gather_strips_to_rank0(color, depth, height: int, group=None):
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+
+class TorchFrameBuffer:
+    """Device framebuffer whose memory is owned by torch tensors (`color` (frames,H,W,4) uint8,
+    `depth` (frames,H,W) float32) and wrapped for the C ABI (`grb_framebuffer_wrap`) — what the
+    NCCL gather of the strip mode operates on."""
+
+    def __init__(self, width: int, height: int, frames: int, device, torch_device):
+        import torch
+
+        from .renderer import FrameBuffer
+
+        self.color = torch.empty((frames, height, width, 4), dtype=torch.uint8, device=torch_device)
+        self.depth = torch.empty((frames, height, width), dtype=torch.float32, device=torch_device)
+        self.fb = FrameBuffer(width, height, frames, device, device_color=self.color.data_ptr(),
+                              device_depth=self.depth.data_ptr())
+
+
+def draw_strip(renderer, packed, height: int, world_size: int, rank: int, frame0: int = 0):
+    """Rasterise this rank's strip of the frame described by `packed` (grb_object[1][nobj]).
+    Returns the row range, or None when the rank owns no rows."""
+    y0, y1 = strip_rows(height, world_size, rank)
+    if y1 <= y0:
+        return None
+    renderer.draw_packed(packed, frame0, rows=(y0, y1), sync=False)
+    return y0, y1
+
+
+def frame_parallel_blocks(num_poses: int, world_size: int) -> List[Tuple[int, int]]:
+    return [pose_block(num_poses, world_size, r) for r in range(world_size)]

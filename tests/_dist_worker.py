@@ -1,0 +1,95 @@
+"""Worker for the world_size>1 tests (launched with torch.distributed.run).
+
+mode "gloo": CPU, host-side logic only — every rank produces its strip of a frame with the
+  oracle, strips are gathered to rank 0 with the product's gather_strips_to_rank0 and compared
+  with the whole-frame oracle render; pose blocks are checked to tile the batch.
+mode "nccl": GPU — the same through the CUDA path (strip draws into torch-owned framebuffers,
+  NCCL gather over NVLink), plus a frame-parallel batch compared per rank with the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import gorender_b200 as g  # noqa: E402
+from gorender_b200 import parallel, workloads  # noqa: E402
+from oracle_binding import Oracle  # noqa: E402
+import scene_defs  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    orc = Oracle()
+    sc = scene_defs.multi_object()
+    H, W = sc.height, sc.width
+
+    if mode == "gloo":
+        dist.init_process_group("gloo")
+        r = sc.renderer(None)
+        ref = orc.draw(r, sc.objects, sc.camera)
+        color = torch.zeros((H, W, 4), dtype=torch.uint8)
+        depth = torch.zeros((H, W), dtype=torch.float32)
+        y0, y1 = parallel.strip_rows(H, world, rank)
+        color[y0:y1] = torch.from_numpy(ref["pixels"][y0:y1])
+        depth[y0:y1] = torch.from_numpy(ref["zbuffer"][y0:y1])
+        parallel.gather_strips_to_rank0(color, depth, H)
+        if rank == 0:
+            assert np.array_equal(color.numpy(), ref["pixels"])
+            assert np.array_equal(depth.numpy().view(np.uint32), ref["zbuffer"].view(np.uint32))
+        # frame-parallel partition: blocks tile the batch
+        b, e = parallel.pose_block(37, world, rank)
+        t = torch.tensor([b, e], dtype=torch.int64)
+        out = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(out, t)
+        blocks = [tuple(x.tolist()) for x in out]
+        assert blocks == parallel.frame_parallel_blocks(37, world), blocks
+        assert blocks[0][0] == 0 and blocks[-1][1] == 37
+        dist.barrier()
+        dist.destroy_process_group()
+        print(f"rank {rank} ok")
+        return
+
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    dev = g.Device(local, stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        # ---- sort-first strips, gathered to rank 0 over NCCL
+        tfb = parallel.TorchFrameBuffer(W, H, 1, dev, torch.device("cuda", local))
+        tfb.color.zero_()
+        tfb.depth.zero_()
+        r = sc.renderer(tfb.fb)
+        packed = r.pack_objects(sc.objects, [sc.camera])
+        parallel.draw_strip(r, packed, H, world, rank)
+        parallel.gather_strips_to_rank0(tfb.color[0], tfb.depth[0], H)
+        stream.synchronize()
+        if rank == 0:
+            ref = orc.draw(r, sc.objects, sc.camera)
+            assert np.array_equal(tfb.color[0].cpu().numpy(), ref["pixels"]), "gathered colour differs"
+            assert np.array_equal(tfb.depth[0].cpu().numpy().view(np.uint32), ref["zbuffer"].view(np.uint32))
+        # ---- frame-parallel: each rank renders its block of poses
+        objs, cams = workloads.config_c5(n=16, poses=10)
+        b, e = parallel.pose_block(len(cams), world, rank)
+        fb = g.FrameBuffer(640, 360, max(e - b, 1), dev)
+        rr = g.Renderer(fb)
+        if e > b:
+            px, z, tpf = rr.DrawBatch(objs, cams[b:e])
+            for k in (0, e - b - 1):
+                ref = orc.draw(rr, objs, cams[b + k])
+                assert int(tpf[k]) == ref["tpf"]
+                assert np.array_equal(px[k], ref["pixels"]) and np.array_equal(z[k].view(np.uint32), ref["zbuffer"].view(np.uint32))
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank} ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -275,6 +275,32 @@ class Oracle:
                 self.lib.orc_renderer_destroy(r)
         return out
 
+    def sequence_timer(self, renderer, objects, cameras, rotations_y=None, threads=16):
+        """Persistent renderer + marshalled frames; `run(first, count)` times `count` consecutive
+        Draw calls in C and returns (seconds, tpf of the last frame)."""
+        fb = renderer.fb
+        m = self.marshal(renderer, objects, cameras, rotations_y)
+        r = self.lib.orc_renderer_create(fb.Width, fb.Height, renderer.numTiles, threads)
+        assert r
+        lib = self.lib
+        stride = C.sizeof(orc_object) * max(m["nobj"], 1)
+
+        class Timer:
+            def run(self_, first, count):
+                assert 0 <= first and first + count <= m["nframes"]
+                objs = C.cast(C.c_void_p(C.addressof(m["objs"]) + first * stride), C.POINTER(orc_object))
+                sec = lib.orc_renderer_draw_sequence(r, m["meshes"], m["nmesh"], m["textures"], m["ntex"], objs,
+                                                     m["nobj"], count, _fp(m["screen"]), _fp(m["light"]), m["options"])
+                assert sec >= 0
+                return float(sec), int(lib.orc_renderer_tpf(r))
+
+            def close(self_):
+                lib.orc_renderer_destroy(r)
+
+        t = Timer()
+        t._keep = m
+        return t
+
     def time_sequence(self, renderer, objects, cameras, rotations_y=None, threads=16, warmup=2):
         """Seconds (measured in C) for len(cameras) consecutive Draw calls in the reference's
         threaded structure; the timed CPU baseline of bench.py.  Returns (seconds, frames, tpf)."""
