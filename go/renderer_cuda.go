@@ -1,0 +1,227 @@
+//go:build cuda
+
+// renderer_cuda.go — the cgo shim that puts gorender's per-frame hot path on a B200.
+//
+// Drop this file (and gorender_b200.h + libgorender_b200.so) next to the reference's sources,
+// add `//go:build !cuda` to the top of a file holding the reference's own
+// `func (r *Renderer) Draw` (renderer.go:443-483), and build with
+//
+//	CGO_ENABLED=1 go build -tags cuda -o gorender
+//
+// Nothing else changes: NewFrameBuffer, NewRenderer, the option fields, Camera, Object, Mesh,
+// LoadObjFile, LoadSceneFile and Texture keep their reference definitions, and matrix.go keeps
+// building the per-object matrices on the host (so Go's math.Sin/Cos/Tan are the ones used).
+// Draw keeps its signature — no return value, results are side effects on fb.Pixels,
+// fb.ZBuffer and r.TPF — and, like the reference, cannot fail: a non-zero status panics.
+//
+// NOTE: the Go toolchain is not available where this repository is developed; this file is
+// written against include/gorender_b200.h and mirrors, call for call, the Python binding
+// (gorender_b200/renderer.py) that the GPU parity tests exercise.
+package main
+
+/*
+#cgo CFLAGS: -I${SRCDIR}
+#cgo LDFLAGS: -L${SRCDIR} -lgorender_b200 -Wl,-rpath,${SRCDIR}
+#include <stdlib.h>
+#include "gorender_b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"sync"
+	"unsafe"
+)
+
+// cudaRenderer is the per-Renderer device state (one grb_context == one GPU).
+type cudaRenderer struct {
+	ctx      *C.grb_context
+	fb       *C.grb_framebuffer
+	meshes   map[*Mesh]C.int32_t
+	textures map[*Texture]C.int32_t
+	objs     []C.grb_object
+}
+
+var (
+	cudaStates   = map[*Renderer]*cudaRenderer{}
+	cudaStatesMu sync.Mutex
+)
+
+func cudaCheck(ctx *C.grb_context, rc C.int32_t, what string) {
+	if rc != C.GRB_OK {
+		panic(fmt.Sprintf("gorender_b200: %s: %s", what, C.GoString(C.grb_last_error(ctx))))
+	}
+}
+
+func (r *Renderer) cuda() *cudaRenderer {
+	cudaStatesMu.Lock()
+	defer cudaStatesMu.Unlock()
+	if s, ok := cudaStates[r]; ok {
+		return s
+	}
+	s := &cudaRenderer{meshes: map[*Mesh]C.int32_t{}, textures: map[*Texture]C.int32_t{}}
+	cudaCheck(nil, C.grb_context_create(0, &s.ctx), "grb_context_create")
+	cudaCheck(s.ctx, C.grb_framebuffer_create(s.ctx, C.int32_t(r.fb.Width), C.int32_t(r.fb.Height), 1, &s.fb),
+		"grb_framebuffer_create")
+	cudaStates[r] = s
+	return s
+}
+
+// textureID uploads a Texture once (texture.go:19-26 fields) and returns its device id; nil -> -1.
+func (s *cudaRenderer) textureID(t *Texture) C.int32_t {
+	if t == nil {
+		return -1
+	}
+	if id, ok := s.textures[t]; ok {
+		return id
+	}
+	var id C.int32_t
+	col := [4]C.uint8_t{C.uint8_t(t.color.R), C.uint8_t(t.color.G), C.uint8_t(t.color.B), C.uint8_t(t.color.A)}
+	var px *C.uint8_t
+	if len(t.pixels) > 0 {
+		px = (*C.uint8_t)(unsafe.Pointer(&t.pixels[0])) // color.RGBA is 4 x uint8, R,G,B,A
+	}
+	cudaCheck(s.ctx, C.grb_texture_upload(s.ctx, C.int32_t(t.typ), C.int32_t(t.width), C.int32_t(t.height),
+		C.float(t.scale), &col[0], px, &id), "grb_texture_upload")
+	s.textures[t] = id
+	return id
+}
+
+// meshID flattens a Mesh (mesh.go:12-26: Face holds a Go pointer and 64-bit ints, so it cannot
+// cross cgo as is) and uploads it once.
+func (s *cudaRenderer) meshID(m *Mesh) C.int32_t {
+	if id, ok := s.meshes[m]; ok {
+		return id
+	}
+	nf := len(m.Faces)
+	vidx := make([]int32, 3*nf)
+	nidx := make([]int32, 3*nf)
+	uvs := make([]float32, 6*nf)
+	tex := make([]int32, nf)
+	for i := range m.Faces {
+		f := &m.Faces[i]
+		for k := 0; k < 3; k++ {
+			vidx[3*i+k] = int32(f.VertexIndices[k])
+			nidx[3*i+k] = int32(f.NormalIndices[k])
+			uvs[6*i+2*k] = f.UVs[k].U
+			uvs[6*i+2*k+1] = f.UVs[k].V
+		}
+		tex[i] = int32(s.textureID(f.Texture))
+	}
+	var d C.grb_mesh_desc
+	d.nv, d.nvn, d.nf = C.int32_t(len(m.Vertices)), C.int32_t(len(m.VertexNormals)), C.int32_t(nf)
+	// The descriptor's pointers refer to Go memory: pin them for the duration of the call.
+	var pin runtimePinner
+	defer pin.Unpin()
+	d.vertices = (*C.float)(pin.ptr(unsafe.Pointer(&m.Vertices[0])))
+	if len(m.VertexNormals) > 0 {
+		d.vnormals = (*C.float)(pin.ptr(unsafe.Pointer(&m.VertexNormals[0])))
+		d.nidx = (*C.int32_t)(pin.ptr(unsafe.Pointer(&nidx[0])))
+	}
+	if nf > 0 {
+		d.fnormals = (*C.float)(pin.ptr(unsafe.Pointer(&m.FaceNormals[0])))
+		d.vidx = (*C.int32_t)(pin.ptr(unsafe.Pointer(&vidx[0])))
+		d.uvs = (*C.float)(pin.ptr(unsafe.Pointer(&uvs[0])))
+		d.tex = (*C.int32_t)(pin.ptr(unsafe.Pointer(&tex[0])))
+	}
+	for c := 0; c < 8; c++ {
+		d.bbox[4*c+0] = C.float(m.BoundingBox[c].X)
+		d.bbox[4*c+1] = C.float(m.BoundingBox[c].Y)
+		d.bbox[4*c+2] = C.float(m.BoundingBox[c].Z)
+		d.bbox[4*c+3] = C.float(m.BoundingBox[c].W)
+	}
+	var id C.int32_t
+	cudaCheck(s.ctx, C.grb_mesh_upload(s.ctx, &d, &id), "grb_mesh_upload")
+	s.meshes[m] = id
+	return id
+}
+
+func matrixToC(dst *[16]C.float, m *Matrix) {
+	for i := 0; i < 4; i++ {
+		for j := 0; j < 4; j++ {
+			dst[4*i+j] = C.float(m[i][j])
+		}
+	}
+}
+
+func (r *Renderer) optionBits() C.uint32_t {
+	var o C.uint32_t
+	if r.FrustumClipping {
+		o |= C.GRB_OPT_FRUSTUM_CLIPPING
+	}
+	if r.ShowFaces {
+		o |= C.GRB_OPT_SHOW_FACES
+	}
+	if r.BackfaceCulling {
+		o |= C.GRB_OPT_BACKFACE_CULLING
+	}
+	if r.Lighting {
+		o |= C.GRB_OPT_LIGHTING
+	}
+	if r.FlatShading {
+		o |= C.GRB_OPT_FLAT_SHADING
+	}
+	if r.ShowTextures {
+		o |= C.GRB_OPT_SHOW_TEXTURES
+	}
+	return o
+}
+
+// Draw replaces renderer.go:443-483.  Host work per object is exactly the reference's
+// renderer.go:255-265 (matrix constructors); everything else happens on the GPU.
+func (r *Renderer) Draw(objects []*Object, camera *Camera) {
+	s := r.cuda()
+
+	viewMatrix := NewViewMatrix(camera.Position, camera.Direction, camera.Up)
+	perspectiveMatrix := NewPerspectiveMatrix(r.fovY, r.aspectX, r.zNear, r.zFar)
+	if cap(s.objs) < len(objects) {
+		s.objs = make([]C.grb_object, len(objects))
+	}
+	objs := s.objs[:len(objects)]
+	for i, object := range objects {
+		worldMatrix := NewWorldMatrix(object.Scale, object.Rotation, object.Translation)
+		mvpMatrix := NewIdentityMatrix()
+		mvpMatrix = mvpMatrix.Multiply(perspectiveMatrix)
+		mvpMatrix = mvpMatrix.Multiply(viewMatrix)
+		mvpMatrix = mvpMatrix.Multiply(worldMatrix)
+		objs[i].mesh = s.meshID(object.Mesh)
+		matrixToC(&objs[i].world, &worldMatrix)
+		matrixToC(&objs[i].mvp, &mvpMatrix)
+	}
+
+	var p C.grb_draw_params
+	screenMatrix := NewScreenMatrix(r.fb.Width, r.fb.Height)
+	matrixToC(&p.screen, &screenMatrix)
+	light := Vec3{X: -1, Y: 1, Z: 1}.Normalize()
+	p.light[0], p.light[1], p.light[2] = C.float(light.X), C.float(light.Y), C.float(light.Z)
+	p.options = r.optionBits()
+	p.z_near, p.z_far = C.float(r.zNear), C.float(r.zFar)
+	p.ref_tiles = C.int32_t(r.numTiles) // 16 (parallel) or 1
+	p.row_begin, p.row_end = 0, 0
+
+	var stats C.grb_frame_stats
+	var objPtr *C.grb_object
+	if len(objs) > 0 {
+		objPtr = &objs[0] // grb_object holds no Go pointers: legal to pass
+	}
+	cudaCheck(s.ctx, C.grb_draw(s.ctx, s.fb, 0, 1, objPtr, C.int32_t(len(objs)), &p, &stats), "grb_draw")
+	r.TPF = int(stats.tpf)
+
+	// FrameBuffer.Pixels / ZBuffer are ordinary Go slices; C writes into them only during the call.
+	cudaCheck(s.ctx, C.grb_read_frames(s.ctx, s.fb, 0, 1,
+		(*C.uint8_t)(unsafe.Pointer(&r.fb.Pixels[0])), (*C.float)(unsafe.Pointer(&r.fb.ZBuffer[0]))),
+		"grb_read_frames")
+}
+
+// matrixMultiplyVec4BatchCUDA is the third implementation behind the reference's build-tag seam
+// (asm_amd64.go:8 / asm_purego.go:9), for callers that want the batch transform alone.
+func matrixMultiplyVec4BatchCUDA(r *Renderer, m *Matrix, vecs []Vec4) {
+	if len(vecs) == 0 {
+		return
+	}
+	s := r.cuda()
+	var mm [16]C.float
+	matrixToC(&mm, m)
+	cudaCheck(s.ctx, C.grb_matrix_multiply_vec4_batch(s.ctx, &mm[0], (*C.float)(unsafe.Pointer(&vecs[0])),
+		C.int64_t(len(vecs))), "grb_matrix_multiply_vec4_batch")
+}
