@@ -59,6 +59,7 @@ struct grb_framebuffer {
 
 struct grb_context {
     int device = 0;
+    int smCount = 148;
     cudaStream_t ownStream = nullptr, stream = nullptr, copyStream = nullptr;
     mutable std::string err;
 
@@ -88,12 +89,13 @@ struct grb_context {
     DevBuf<float4> tv;
     DevBuf<TriRec> rec;
     DevBuf<TriUV> uv;
-    DevBuf<uint32_t> blockBase, tileCount, tileOff, cursor, binList, bigList;
+    DevBuf<uint32_t> warpCount, tileCount, tileOff, tileOffB, cursor, binList, bigList;
     DevBuf<FrameCounters> counters;
     uint32_t recCap = 0;  // per frame
 
     // last draw (for stats / debug read-backs)
     int32_t lastFrames = 0, lastNobj = 0, lastNTiles = 0;
+    uint32_t lastOptions = 0;
     std::vector<int32_t> lastVisibility;
 
     // seam scratch
@@ -225,8 +227,8 @@ int32_t build_plan(grb_context *ctx, const grb_object *objects, int32_t nobj) {
         fblk.insert(fblk.end(), (m.nf + kFaceBlock - 1) / kFaceBlock, i);
     }
     if (verts > INT32_MAX) return fail(ctx, GRB_ERR_INVALID, "draw list has more than 2^31 vertices");
-    if ((int64_t)fblk.size() * kSeqStride >= (int64_t)UINT32_MAX)
-        return fail(ctx, GRB_ERR_INVALID, "draw list has too many faces for 32-bit submission keys");
+    if ((int64_t)fblk.size() * kWarpsPerFaceBlock * kWarpSlotsClip >= (int64_t)UINT32_MAX)
+        return fail(ctx, GRB_ERR_INVALID, "draw list has too many faces for 32-bit record slots");
     ctx->totalVerts = (int32_t)verts;
     ctx->nVertBlocks = (int32_t)vblk.size();
     ctx->nFaceBlocks = (int32_t)fblk.size();
@@ -306,7 +308,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     uint64_t recNeed = 1;
     ctx->lastVisibility.assign((size_t)nframes * nobj, GRB_BOX_OUTSIDE);
     for (int32_t f = 0; f < nframes; f++) {
-        uint64_t need = 0;
+        uint64_t need = 0;  // record slots of this frame: static per-warp segments (setup.cu)
         for (int32_t i = 0; i < nobj; i++) {
             const grb_object &src = objects[(size_t)f * nobj + i];
             FrameObj &dst = hfo[(size_t)f * nobj + i];
@@ -320,11 +322,13 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
             }
             const int vis = box_visibility(corners, prm->z_near, prm->z_far);
             dst.visibility = vis;
+            dst.slotBase = (uint32_t)need;
             ctx->lastVisibility[(size_t)f * nobj + i] = vis;
             if (vis == GRB_BOX_OUTSIDE) continue;
             const bool clips = optClip && vis != GRB_BOX_INSIDE;
             (clips ? anyClip : anyPlain) = true;
-            need += (uint64_t)mh.dev.nf * (clips ? kMaxFan : 1);
+            const uint64_t blocks = (mh.dev.nf + kFaceBlock - 1) / kFaceBlock;
+            need += blocks * kWarpsPerFaceBlock * (clips ? kWarpSlotsClip : kWarpSlots);
         }
         recNeed = std::max(recNeed, need);
     }
@@ -341,15 +345,16 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     if (int32_t r = ensure(ctx, ctx->uv, F * recCap, false)) return r;
     if (int32_t r = ensure(ctx, ctx->bigList, F * recCap, false)) return r;
     if (int32_t r = ensure(ctx, ctx->binList, F * recCap * kMaxBinsPerTri, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->blockBase, F * std::max(ctx->nFaceBlocks, 1), false)) return r;
+    if (int32_t r = ensure(ctx, ctx->warpCount, F * std::max(ctx->nFaceBlocks, 1) * kWarpsPerFaceBlock, false)) return r;
     if (int32_t r = ensure(ctx, ctx->tileOff, F * (nTiles + 1), false)) return r;
+    if (int32_t r = ensure(ctx, ctx->tileOffB, F * nTiles, false)) return r;
     if (int32_t r = ensure(ctx, ctx->cursor, F * nTiles, false)) return r;
     if (int32_t r = ensure(ctx, ctx->counters, F, false)) return r;
     ctx->recCap = recCap;
     // tile counters must be zero on entry; K3 re-zeroes what K2 counted, but the
     // per-frame stride depends on nTiles, so clear when the geometry changes
-    if (ctx->tileCount.cap < F * nTiles || ctx->lastNTiles != nTiles) {
-        if (int32_t r = ensure(ctx, ctx->tileCount, F * nTiles, false)) return r;
+    if (ctx->tileCount.cap < F * 2 * nTiles || ctx->lastNTiles != nTiles) {
+        if (int32_t r = ensure(ctx, ctx->tileCount, F * 2 * nTiles, false)) return r;
         CK(ctx, cudaMemsetAsync(ctx->tileCount.p, 0, ctx->tileCount.cap * sizeof(uint32_t), ctx->stream));
     }
 
@@ -372,9 +377,10 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.tv = ctx->tv.p;
     a.rec = ctx->rec.p;
     a.uv = ctx->uv.p;
-    a.blockBase = ctx->blockBase.p;
+    a.warpCount = ctx->warpCount.p;
     a.tileCount = ctx->tileCount.p;
     a.tileOff = ctx->tileOff.p;
+    a.tileOffB = ctx->tileOffB.p;
     a.cursor = ctx->cursor.p;
     a.binList = ctx->binList.p;
     a.bigList = ctx->bigList.p;
@@ -415,7 +421,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[2], s));
     launch_bin_scan(a, nframes, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[3], s));
-    if (anyVisible) launch_bin_fill(a, nframes, (uint32_t)recNeed, s);
+    if (anyVisible) launch_bin_fill(a, nframes, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[4], s));
     launch_raster(a, nframes, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[5], s));
@@ -439,6 +445,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     ctx->lastFrames = nframes;
     ctx->lastNobj = nobj;
     ctx->lastNTiles = nTiles;
+    ctx->lastOptions = prm->options;
     return GRB_OK;
 }
 
@@ -470,6 +477,7 @@ int32_t grb_context_create(int32_t device, grb_context **out) {
         return fail(nullptr, GRB_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
     }
     ctx->stream = ctx->ownStream;
+    cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess) {
         cudaStreamDestroy(ctx->ownStream);
         delete ctx;
@@ -491,7 +499,7 @@ int32_t grb_context_destroy(grb_context *ctx) {
     for (auto &t : ctx->textures)
         if (t.pixels) cudaFree(t.pixels);
     void *bufs[] = {ctx->dMeshes.p, ctx->dTextures.p, ctx->dObjs.p, ctx->dVblk.p, ctx->dFblk.p, ctx->dFrameObjs.p,
-                    ctx->tv.p, ctx->rec.p, ctx->uv.p, ctx->blockBase.p, ctx->tileCount.p, ctx->tileOff.p,
+                    ctx->tv.p, ctx->rec.p, ctx->uv.p, ctx->warpCount.p, ctx->tileCount.p, ctx->tileOff.p, ctx->tileOffB.p,
                     ctx->cursor.p, ctx->binList.p, ctx->bigList.p, ctx->counters.p, ctx->seam.p};
     for (void *p : bufs)
         if (p) cudaFree(p);
@@ -811,21 +819,38 @@ int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_r
     if (!out) return GRB_OK;
     if (capacity < n) return fail(ctx, GRB_ERR_INVALID, "output too small");
     if (n == 0) return GRB_OK;
-    std::vector<grb_triangle_rec> recs(n);
-    std::vector<TriUV> uvs(n);
-    CK(ctx, cudaMemcpy(recs.data(), ctx->rec.p + (size_t)frame * ctx->recCap, n * sizeof(TriRec), cudaMemcpyDeviceToHost));
-    CK(ctx, cudaMemcpy(uvs.data(), ctx->uv.p + (size_t)frame * ctx->recCap, n * sizeof(TriUV), cudaMemcpyDeviceToHost));
-    // slots are block-ordered, blocks land in atomic order: present in submission order
-    std::vector<int64_t> order(n);
-    for (int64_t i = 0; i < n; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return recs[x].seq1 < recs[y].seq1; });
-    for (int64_t i = 0; i < n; i++) {
-        out[i] = recs[order[i]];
-        if (out_uvs) {
-            if (recs[order[i]].tex >= 0) std::memcpy(out_uvs + 6 * i, &uvs[order[i]], 24);
-            else std::memset(out_uvs + 6 * i, 0, 24);
+    // records sit in per-warp segments in submission order (setup.cu); walk them with the
+    // per-warp counts, exactly as bin_fill_kernel does
+    const int32_t nobj = ctx->lastNobj;
+    const size_t nWarps = (size_t)ctx->nFaceBlocks * kWarpsPerFaceBlock;
+    std::vector<uint32_t> wc(nWarps);
+    std::vector<FrameObj> fo(std::max(nobj, 1));
+    CK(ctx, cudaMemcpy(wc.data(), ctx->warpCount.p + (size_t)frame * nWarps, nWarps * 4, cudaMemcpyDeviceToHost));
+    if (nobj) CK(ctx, cudaMemcpy(fo.data(), ctx->dFrameObjs.p + (size_t)frame * nobj, nobj * sizeof(FrameObj), cudaMemcpyDeviceToHost));
+    const bool optClip = ctx->lastOptions & GRB_OPT_FRUSTUM_CLIPPING;
+    int64_t k = 0;
+    for (int32_t i = 0; i < nobj && k < n; i++) {
+        if (fo[i].visibility == GRB_BOX_OUTSIDE) continue;
+        const bool clips = optClip && fo[i].visibility != GRB_BOX_INSIDE;
+        const uint32_t perWarp = clips ? kWarpSlotsClip : kWarpSlots;
+        const DrawObj &ob = ctx->planObjs[i];
+        const int32_t nf = ctx->meshes[ob.mesh].dev.nf;
+        const int32_t blocks = (nf + kFaceBlock - 1) / kFaceBlock;
+        for (int64_t w = 0; w < (int64_t)blocks * kWarpsPerFaceBlock && k < n; w++) {
+            const uint32_t cnt = wc[(size_t)ob.faceBlockBase * kWarpsPerFaceBlock + w];
+            if (cnt == 0) continue;
+            if (k + cnt > n) return fail(ctx, GRB_ERR_STATE, "record walk disagrees with the triangle counter");
+            const size_t slot = (size_t)frame * ctx->recCap + fo[i].slotBase + (size_t)w * perWarp;
+            CK(ctx, cudaMemcpy(out + k, ctx->rec.p + slot, cnt * sizeof(TriRec), cudaMemcpyDeviceToHost));
+            if (out_uvs) {
+                CK(ctx, cudaMemcpy(out_uvs + 6 * k, ctx->uv.p + slot, cnt * sizeof(TriUV), cudaMemcpyDeviceToHost));
+                for (uint32_t j = 0; j < cnt; j++)
+                    if (out[k + j].tex < 0) std::memset(out_uvs + 6 * (k + j), 0, 24);
+            }
+            k += cnt;
         }
     }
+    if (k != n) return fail(ctx, GRB_ERR_STATE, "record walk disagrees with the triangle counter");
     return GRB_OK;
 }
 

@@ -7,10 +7,12 @@
 //   tv        [frames][totalVerts]        float4   clip-space vertices        (K1 -> K2)
 //   rec       [frames][recCap]            TriRec   emitted triangles, 64 B    (K2 -> K4,K5)
 //   uv        [frames][recCap]            TriUV    24 B, textured faces only  (K2 -> K5)
-//   blockBase [frames][nFaceBlocks]       u32      first rec slot of a block  (K2 -> K5)
-//   tileCount [frames][nTiles]            u32      (K2 -> K3; K3 re-zeroes)
-//   tileOff   [frames][nTiles+1]          u32      (K3 -> K4,K5)
-//   cursor    [frames][nTiles]            u32      (K3 zeroes -> K4)
+//   warpCount [frames][nFaceBlocks*8]     u32      triangles emitted by a warp (K2 -> K4)
+//   tileCount [frames][2][nTiles]         u32      A: first-tile entries (positions handed out
+//                                                  in K2), B: other tiles   (K2 -> K3; K3 re-zeroes)
+//   tileOff   [frames][nTiles+1]          u32      list start per tile       (K3 -> K4,K5)
+//   tileOffB  [frames][nTiles]            u32      start of the B part       (K3 -> K4)
+//   cursor    [frames][nTiles]            u32      B-part cursor (K3 zeroes -> K4)
 //   binList   [frames][kMaxBinsPerTri*recCap] u32  rec slots per tile         (K4 -> K5)
 //   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles
 //   counters  [frames]                    FrameCounters
@@ -26,7 +28,9 @@ namespace gr {
 constexpr int kTile = GRB_TILE;            // raster tile edge (pixels)
 constexpr int kTilePix = kTile * kTile;
 constexpr int kFaceBlock = 256;            // faces per setup block
-constexpr int kSeqStride = 2048;           // order keys reserved per face block (>= 7*256)
+constexpr int kWarpsPerFaceBlock = kFaceBlock / 32;
+constexpr int kWarpSlots = 32;             // rec slots reserved per warp, objects that do not clip
+constexpr int kWarpSlotsClip = 256;        // ... objects that clip (<= 7 triangles per face)
 constexpr int kMaxFan = 7;                 // clipping.go:10: <= 9 vertices -> <= 7 triangles
 constexpr int kMaxBinsPerTri = 16;         // more tiles than this -> bigList
 constexpr int kCoordLimit = 16383;         // |snapped coord| bound of the int32 edge-function domain
@@ -55,7 +59,8 @@ struct FrameObj {
     float mvp[16];
     float world[16];
     int32_t visibility;      // GRB_BOX_*
-    int32_t pad[3];
+    uint32_t slotBase;       // first rec slot of this object in this frame
+    int32_t pad[2];
 };
 
 // per object of the draw list (same for every frame of a batch)
@@ -73,7 +78,7 @@ struct __align__(16) TriRec {   // == grb_triangle_rec, 64 B
     float w2, i0, i1, i2;
     int16_t bx0, by0, bx1, by1;
     int32_t tex;
-    uint32_t seq1;
+    uint32_t binPos;         // position in the list of the triangle's first device tile
 };
 static_assert(sizeof(TriRec) == 64, "TriRec must be 64 bytes");
 static_assert(sizeof(grb_triangle_rec) == 64, "ABI record must be 64 bytes");
@@ -111,9 +116,10 @@ struct DrawArgs {
     float4 *tv;
     TriRec *rec;
     TriUV *uv;
-    uint32_t *blockBase;
+    uint32_t *warpCount;
     uint32_t *tileCount;
     uint32_t *tileOff;
+    uint32_t *tileOffB;
     uint32_t *cursor;
     uint32_t *binList;
     uint32_t *bigList;

@@ -14,7 +14,7 @@ void launch_setup(const DrawArgs &a, int nframes, bool anyPlain, bool anyClip, c
 // K3: exclusive scan of the per-tile counts (one block per frame).
 void launch_bin_scan(const DrawArgs &a, int nframes, cudaStream_t s);
 // K4: scatter triangle slots into the per-tile lists.
-void launch_bin_fill(const DrawArgs &a, int nframes, uint32_t maxTris, cudaStream_t s);
+void launch_bin_fill(const DrawArgs &a, int nframes, cudaStream_t s);
 // K5: per-tile coverage + z resolve in shared memory, shade, coalesced write-back.
 void launch_raster(const DrawArgs &a, int nframes, cudaStream_t s);
 // matrixMultiplyVec4Batch over a device array.

@@ -21,12 +21,15 @@
 // operation follow the reference's order; results are bit-identical to the
 // serial CPU path.
 
+#include <algorithm>
+
 #include "gr_types.cuh"
 #include "kernels.h"
 
 namespace gr {
 
 constexpr int kRasterThreads = 256;
+constexpr int kRasterBlocksPerSM = 6;  // resident blocks per SM the register budget is held to
 constexpr int kSmallArea = 32;  // bbox∩tile pixels up to which one thread rasterises a triangle alone
 constexpr unsigned long long kBackgroundKey = 0x407FFFFFull << 32;  // orderable(-1.0f) (rasterizer.go:37)
 
@@ -67,8 +70,10 @@ __device__ __forceinline__ float z_reciprocal(float alpha, float beta, float gam
     return -fadd(fadd(fdiv(alpha, z0), fdiv(beta, z1)), fdiv(gamma, z2));
 }
 
-__device__ __forceinline__ unsigned long long fragment_key(float zrec, uint32_t seq1) {
-    return ((unsigned long long)orderable(zrec) << 32) | seq1;
+// The record slot is the submission order (setup.cu): key = depth | slot + 1; 0 in the low
+// word marks the cleared background.
+__device__ __forceinline__ unsigned long long fragment_key(float zrec, uint32_t slot) {
+    return ((unsigned long long)orderable(zrec) << 32) | (slot + 1u);
 }
 
 // Go `int(f)` on amd64 (CVTTSS2SQ): truncation, INT64_MIN when out of range / NaN.
@@ -102,30 +107,46 @@ __device__ __forceinline__ uchar4 sample_texture(const TexDev &t, float u, float
     return __ldg(&t.pixels[idx]);
 }
 
-// One thread rasterises one small triangle into the tile (rasterizer.go:140-182,
-// visibility part only).
-__device__ __forceinline__ void raster_small(const TriRec &r, int x0, int y0, int x1, int y1, int tileX, int tileY,
-                                             unsigned long long *keys) {
-    const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
-    int row01 = e.a01 * x0 + e.b01 * y0 + e.c01;
-    int row12 = e.a12 * x0 + e.b12 * y0 + e.c12;
-    int row20 = e.a20 * x0 + e.b20 * y0 + e.c20;
-    for (int y = y0; y <= y1; y++) {
-        int f01 = row01, f12 = row12, f20 = row20;
-        for (int x = x0; x <= x1; x++) {
-            if ((f01 & f12 & f20) < 0) {  // all three negative
-                float al, be, ga;
-                barycentric(f01, f12, f20, al, be, ga);
-                const float z = z_reciprocal(al, be, ga, r.w0, r.w1, r.w2);
-                if (z >= -1.0f) {  // can ever pass `zRec >= ZBuffer` (cleared to -1); false for NaN
-                    const unsigned long long key = fragment_key(z, r.seq1);
-                    unsigned long long *p = &keys[(y - tileY) * kTile + (x - tileX)];
-                    if (key > *(volatile unsigned long long *)p) atomicMax(p, key);
-                }
-            }
-            f01 += e.a01; f12 += e.a12; f20 += e.a20;
+// ---- small triangles: warp-cooperative coarse / fine rasterisation ---------------------------
+//
+// A warp takes 32 list entries at a time.  Each lane sets up its triangle (edge functions, the
+// bbox clipped to the tile) into a per-warp shared-memory table, struct-of-arrays so that lanes
+// reading different triangles hit different banks.  The bbox pixels of all 32 triangles are then
+// flattened into one work list (warp prefix sum of the areas) and tested 32 at a time — coarse
+// stage, integer edge functions only.  Covered (triangle, pixel) pairs are pushed into a
+// per-warp ring; whenever 32 are available the fine stage runs with every lane busy: 5 IEEE
+// divides for zRec (rasterizer.go:149-153) and a shared-memory atomic max on the pixel's key.
+// One lane per triangle would execute the divide sequence at the occupancy of the rare covered
+// pixels; this way the expensive part runs dense.
+
+struct WarpTris {            // one per warp, 32 triangles
+    int a01[32], b01[32], c01[32];
+    int a12[32], b12[32], c12[32];
+    int a20[32], b20[32], c20[32];
+    float w0[32], w1[32], w2[32];
+    uint32_t slot[32];
+    uint32_t box[32];        // local x0 | local y0 << 5 | (bw-1) << 10
+};
+constexpr int kFragRing = 64;
+
+// fine stage for `count` (<= 32) queued fragments starting at ring position `head`
+__device__ __forceinline__ void fine_stage(const WarpTris &wt, const uint32_t *ring, uint32_t head, int count, int lane,
+                                           int tileX, int tileY, unsigned long long *keys) {
+    if (lane < count) {
+        const uint32_t f = ring[(head + lane) & (kFragRing - 1)];
+        const int t = f >> 10, lx = f & 31, ly = (f >> 5) & 31;
+        const int x = tileX + lx, y = tileY + ly;
+        const int f01 = wt.a01[t] * x + wt.b01[t] * y + wt.c01[t];
+        const int f12 = wt.a12[t] * x + wt.b12[t] * y + wt.c12[t];
+        const int f20 = wt.a20[t] * x + wt.b20[t] * y + wt.c20[t];
+        float al, be, ga;
+        barycentric(f01, f12, f20, al, be, ga);
+        const float z = z_reciprocal(al, be, ga, wt.w0[t], wt.w1[t], wt.w2[t]);
+        if (z >= -1.0f) {  // can ever pass `zRec >= ZBuffer` (cleared to -1); false for NaN
+            const unsigned long long key = fragment_key(z, wt.slot[t]);
+            unsigned long long *p = &keys[ly * kTile + lx];
+            if (key > *(volatile unsigned long long *)p) atomicMax(p, key);
         }
-        row01 += e.b01; row12 += e.b12; row20 += e.b20;
     }
 }
 
@@ -137,113 +158,265 @@ __device__ __forceinline__ TriRec load_rec(const TriRec *p) {
     return r;
 }
 
-__global__ void __launch_bounds__(kRasterThreads) raster_kernel(const __grid_constant__ DrawArgs a) {
+// Clear (rasterizer.go:36-44) + DotGrid step 10 (:46-52) for one pixel.
+__device__ __forceinline__ uchar4 background(int x, int y) {
+    const bool dot = (x >= 10) && (y >= 10) && (x % 10 == 0) && (y % 10 == 0);
+    return dot ? make_uchar4(100, 100, 100, 255) : make_uchar4(50, 50, 50, 255);
+}
+
+// Four consecutive pixels of one row: one 128-bit store each for colour and depth.
+__device__ __forceinline__ void write_quad(const DrawArgs &a, int frame, int gx, int gy, const uchar4 col[4],
+                                           const float zo[4]) {
+    const size_t pix = ((size_t)frame * a.height + gy) * a.width + gx;
+    if ((a.width & 3) == 0) {
+        // gx is a multiple of 4 and so is width: 16-byte aligned, whole quad in range
+        uint4 cq;
+        cq.x = *reinterpret_cast<const uint32_t *>(&col[0]); cq.y = *reinterpret_cast<const uint32_t *>(&col[1]);
+        cq.z = *reinterpret_cast<const uint32_t *>(&col[2]); cq.w = *reinterpret_cast<const uint32_t *>(&col[3]);
+        *reinterpret_cast<uint4 *>(a.color + pix) = cq;
+        *reinterpret_cast<float4 *>(a.depth + pix) = make_float4(zo[0], zo[1], zo[2], zo[3]);
+    } else {
+        for (int k = 0; k < 4 && gx + k < a.width; k++) {
+            a.color[pix + k] = col[k];
+            a.depth[pix + k] = zo[k];
+        }
+    }
+}
+
+// Large triangle staged in shared memory for the cooperative pass: edge functions set up once
+// by the thread that queued it.
+struct __align__(16) CoopTri {
+    int a01, b01, c01, a12;
+    int b12, c12, a20, b20;
+    int c20;
+    float w0, w1, w2;
+    int16_t bx0, by0, bx1, by1;
+    uint32_t slot;
+    uint32_t pad;
+};
+static_assert(sizeof(CoopTri) == 64, "CoopTri must be 64 bytes");
+
+__global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_kernel(const __grid_constant__ DrawArgs a) {
     __shared__ unsigned long long keys[kTilePix];
-    __shared__ uint32_t queue[kRasterThreads];
+    // pass 1 (small triangles) and pass 2 (large ones) never overlap: their tables share storage
+    __shared__ __align__(16) unsigned char scratch[sizeof(CoopTri) * kRasterThreads];
+    __shared__ uint32_t fragRing[kRasterThreads / 32][kFragRing];
     __shared__ int queueCount;
+    static_assert(sizeof(WarpTris) * (kRasterThreads / 32) <= sizeof(scratch), "scratch too small");
+    CoopTri *queue = reinterpret_cast<CoopTri *>(scratch);
+
+    const int tid = threadIdx.x;
+    const int nTiles = a.ntx * a.nty;
+    // pixels owned by this thread inside the tile: 4 consecutive in x
+    const int px = (tid & 7) * 4, py = tid >> 3;
 
     const int frame = blockIdx.z;
     const int tx = blockIdx.x, ty = blockIdx.y + a.tileRowBegin;
     const int tile = ty * a.ntx + tx;
-    const int nTiles = a.ntx * a.nty;
     const int tileX = tx * kTile, tileY = ty * kTile;
-    const int tileX1 = min(tileX + kTile, a.width) - 1, tileY1 = min(tileY + kTile, a.height) - 1;
-    const int tid = threadIdx.x;
 
-    const TriRec *rec = a.rec + (size_t)frame * a.recCap;
     const uint32_t *off = a.tileOff + (size_t)frame * (nTiles + 1);
-    const uint32_t listBegin = off[tile], listEnd = off[tile + 1];
-    const uint32_t *list = a.binList + (size_t)frame * a.recCap * kMaxBinsPerTri;
+    const uint32_t listBegin = off[tile], nList = off[tile + 1] - listBegin;
     const uint32_t nBig = a.counters[frame].bigCount;
-    const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
 
-    // pixels owned by this thread: 4 consecutive in x
-    const int px = (tid & 7) * 4, py = tid >> 3;
+    const int gx = tileX + px, gy = tileY + py;
+    const bool inImage = gy < a.height && gx < a.width;
+
+    // ---- nothing touches this tile: cleared background straight to HBM (block-uniform branch)
+    if (nList == 0 && nBig == 0) {
+        if (inImage) {
+            uchar4 col[4];
+            float zo[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                col[k] = background(gx + k, gy);
+                zo[k] = -1.0f;
+            }
+            write_quad(a, frame, gx, gy, col, zo);
+        }
+        return;
+    }
+
+    const int tileX1 = min(tileX + kTile, a.width) - 1, tileY1 = min(tileY + kTile, a.height) - 1;
+    const TriRec *rec = a.rec + (size_t)frame * a.recCap;
+    const uint32_t *list = a.binList + (size_t)frame * a.recCap * kMaxBinsPerTri + listBegin;
+    const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
 
     for (int i = tid; i < kTilePix; i += kRasterThreads) keys[i] = kBackgroundKey;
     if (tid == 0) queueCount = 0;
     __syncthreads();
 
-    // ------------------------------------------------------------ phase A
-    const uint32_t nList = listEnd - listBegin;
-    const uint32_t nWork = nList + nBig;
-    for (uint32_t base = 0; base < nWork; base += kRasterThreads) {
-        const uint32_t i = base + tid;
-        if (i < nWork) {
-            const uint32_t slot = i < nList ? list[listBegin + i] : big[i - nList];
-            const TriRec r = load_rec(rec + slot);
-            const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
-            const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
-            if (x0 <= x1 && y0 <= y1) {
-                if ((x1 - x0 + 1) * (y1 - y0 + 1) <= kSmallArea)
-                    raster_small(r, x0, y0, x1, y1, tileX, tileY, keys);
-                else
-                    queue[atomicAdd(&queueCount, 1)] = slot;
-            }
-        }
-        __syncthreads();
-        const int nq = queueCount;
-        if (nq) {
-            // large triangles: the whole block, thread-owned pixels, no atomics
-            unsigned long long k0 = keys[py * kTile + px], k1 = keys[py * kTile + px + 1];
-            unsigned long long k2 = keys[py * kTile + px + 2], k3 = keys[py * kTile + px + 3];
-            const int gx = tileX + px, gy = tileY + py;
-            for (int q = 0; q < nq; q++) {
-                const TriRec r = load_rec(rec + queue[q]);
-                if (gy < r.by0 || gy > r.by1 || gx > r.bx1 || gx + 3 < r.bx0) continue;
-                const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
-                int f01 = e.a01 * gx + e.b01 * gy + e.c01;
-                int f12 = e.a12 * gx + e.b12 * gy + e.c12;
-                int f20 = e.a20 * gx + e.b20 * gy + e.c20;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int x = gx + k;
-                    if ((f01 & f12 & f20) < 0 && x >= r.bx0 && x <= r.bx1) {
-                        float al, be, ga;
-                        barycentric(f01, f12, f20, al, be, ga);
-                        const float z = z_reciprocal(al, be, ga, r.w0, r.w1, r.w2);
-                        if (z >= -1.0f) {
-                            const unsigned long long key = fragment_key(z, r.seq1);
-                            if (k == 0) k0 = max(k0, key);
-                            if (k == 1) k1 = max(k1, key);
-                            if (k == 2) k2 = max(k2, key);
-                            if (k == 3) k3 = max(k3, key);
-                        }
+    // ------------------------------------------------------------ phase A, pass 1
+    // small triangles, one thread each, no barriers; large ones are only counted
+    int nLarge = 0;
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const unsigned ltMask = (1u << lane) - 1u;
+        WarpTris &wt = reinterpret_cast<WarpTris *>(scratch)[warp];
+        uint32_t *ring = fragRing[warp];
+        uint32_t qHead = 0, qTail = 0;  // warp-uniform
+        for (uint32_t base = warp * 32; base < nList; base += kRasterThreads) {
+            const uint32_t i = base + lane;
+            int area = 0;
+            if (i < nList) {
+                const uint32_t slot = list[i];
+                const TriRec r = load_rec(rec + slot);
+                const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
+                const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
+                if (x0 <= x1 && y0 <= y1) {
+                    const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
+                    if (n <= kSmallArea) {
+                        const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+                        wt.a01[lane] = e.a01; wt.b01[lane] = e.b01; wt.c01[lane] = e.c01;
+                        wt.a12[lane] = e.a12; wt.b12[lane] = e.b12; wt.c12[lane] = e.c12;
+                        wt.a20[lane] = e.a20; wt.b20[lane] = e.b20; wt.c20[lane] = e.c20;
+                        wt.w0[lane] = r.w0; wt.w1[lane] = r.w1; wt.w2[lane] = r.w2;
+                        wt.slot[lane] = slot;
+                        wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)(bw - 1) << 10);
+                        area = n;
+                    } else {
+                        nLarge++;
                     }
-                    f01 += e.a01; f12 += e.a12; f20 += e.a20;
                 }
             }
-            keys[py * kTile + px] = k0; keys[py * kTile + px + 1] = k1;
-            keys[py * kTile + px + 2] = k2; keys[py * kTile + px + 3] = k3;
+            // flatten the 32 bboxes into one pixel list
+            int incl = area;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - area;
+            __syncwarp();
+            for (int item0 = 0; item0 < total; item0 += 32) {
+                const int item = min(item0 + lane, total - 1);
+                // triangle owning this pixel: number of lanes whose inclusive sum is <= item
+                int t = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, t + step - 1);
+                    if (v <= item) t += step;
+                }
+                const int j = item - __shfl_sync(0xffffffffu, excl, t);
+                const uint32_t box = wt.box[t];
+                const int bw = (int)((box >> 10) & 31u) + 1;
+                // j / bw for j < 32: (j + 0.5) / bw is never within 1/64 of an integer
+                const int row = (int)(((float)j + 0.5f) * __frcp_rn((float)bw));
+                const int lx = (int)(box & 31u) + (j - row * bw), ly = (int)((box >> 5) & 31u) + row;
+                const int x = tileX + lx, y = tileY + ly;
+                const int f01 = wt.a01[t] * x + wt.b01[t] * y + wt.c01[t];
+                const int f12 = wt.a12[t] * x + wt.b12[t] * y + wt.c12[t];
+                const int f20 = wt.a20[t] * x + wt.b20[t] * y + wt.c20[t];
+                const bool inside = (item0 + lane < total) && ((f01 & f12 & f20) < 0);
+                const unsigned m = __ballot_sync(0xffffffffu, inside);
+                if (inside) ring[(qTail + __popc(m & ltMask)) & (kFragRing - 1)] = ((uint32_t)t << 10) | ((uint32_t)ly << 5) | (uint32_t)lx;
+                qTail += __popc(m);
+                __syncwarp();
+                if (qTail - qHead >= 32) {
+                    fine_stage(wt, ring, qHead, 32, lane, tileX, tileY, keys);
+                    qHead += 32;
+                }
+            }
+            // the table is rewritten by the next batch: drain what is left
+            if (qTail != qHead) {
+                fine_stage(wt, ring, qHead, (int)(qTail - qHead), lane, tileX, tileY, keys);
+                qHead = qTail;
+            }
+            __syncwarp();
+        }
+    }
+    const int anyLarge = __syncthreads_or(nLarge != 0 || nBig != 0);
+
+    // ------------------------------------------------------------ phase A, pass 2
+    // large triangles (and the big list): the whole block, thread-owned pixels, no atomics
+    if (anyLarge) {
+        const uint32_t nWork = nList + nBig;
+        for (uint32_t base = 0; base < nWork; base += kRasterThreads) {
+            const uint32_t i = base + tid;
+            if (i < nWork) {
+                const uint32_t slot = i < nList ? list[i] : big[i - nList];
+                const int4 q = __ldg(reinterpret_cast<const int4 *>(rec + slot) + 3);
+                const int bx0 = (int16_t)(q.x & 0xffff), by0 = (int16_t)(q.x >> 16);
+                const int bx1 = (int16_t)(q.y & 0xffff), by1 = (int16_t)(q.y >> 16);
+                const int x0 = max(bx0, tileX), x1 = min(bx1, tileX1);
+                const int y0 = max(by0, tileY), y1 = min(by1, tileY1);
+                // list entries with a small footprint were done in pass 1; big-list entries are all done here
+                if (x0 <= x1 && y0 <= y1 && (i >= nList || (x1 - x0 + 1) * (y1 - y0 + 1) > kSmallArea)) {
+                    const TriRec r = load_rec(rec + slot);
+                    const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+                    CoopTri c;
+                    c.a01 = e.a01; c.b01 = e.b01; c.c01 = e.c01;
+                    c.a12 = e.a12; c.b12 = e.b12; c.c12 = e.c12;
+                    c.a20 = e.a20; c.b20 = e.b20; c.c20 = e.c20;
+                    c.w0 = r.w0; c.w1 = r.w1; c.w2 = r.w2;
+                    c.bx0 = (int16_t)x0; c.by0 = (int16_t)y0; c.bx1 = (int16_t)x1; c.by1 = (int16_t)y1;
+                    c.slot = slot;
+                    c.pad = 0;
+                    queue[atomicAdd(&queueCount, 1)] = c;
+                }
+            }
             __syncthreads();
-            if (tid == 0) queueCount = 0;
+            const int nq = queueCount;
+            if (nq) {
+                unsigned long long k0 = keys[py * kTile + px], k1 = keys[py * kTile + px + 1];
+                unsigned long long k2 = keys[py * kTile + px + 2], k3 = keys[py * kTile + px + 3];
+                for (int q = 0; q < nq; q++) {
+                    const CoopTri c = queue[q];  // same address for every thread: broadcast
+                    if (gy < c.by0 || gy > c.by1 || gx > c.bx1 || gx + 3 < c.bx0) continue;
+                    int f01 = c.a01 * gx + c.b01 * gy + c.c01;
+                    int f12 = c.a12 * gx + c.b12 * gy + c.c12;
+                    int f20 = c.a20 * gx + c.b20 * gy + c.c20;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int x = gx + k;
+                        if ((f01 & f12 & f20) < 0 && x >= c.bx0 && x <= c.bx1) {
+                            float al, be, ga;
+                            barycentric(f01, f12, f20, al, be, ga);
+                            const float z = z_reciprocal(al, be, ga, c.w0, c.w1, c.w2);
+                            if (z >= -1.0f) {
+                                const unsigned long long key = fragment_key(z, c.slot);
+                                if (k == 0) k0 = max(k0, key);
+                                if (k == 1) k1 = max(k1, key);
+                                if (k == 2) k2 = max(k2, key);
+                                if (k == 3) k3 = max(k3, key);
+                            }
+                        }
+                        f01 += c.a01; f12 += c.a12; f20 += c.a20;
+                    }
+                }
+                keys[py * kTile + px] = k0; keys[py * kTile + px + 1] = k1;
+                keys[py * kTile + px + 2] = k2; keys[py * kTile + px + 3] = k3;
+                __syncthreads();
+                if (tid == 0) queueCount = 0;
+            }
             __syncthreads();
         }
     }
 
     // ------------------------------------------------------------ phase B
-    const int gx = tileX + px, gy = tileY + py;
-    if (gy >= a.height || gx >= a.width) return;
-
+    if (inImage) {
     uchar4 col[4];
     float zo[4];
-    const uint32_t *blockBase = a.blockBase + (size_t)frame * a.nFaceBlocks;
+    TriRec r;
+    Edges e;
+    uint32_t have = 0;  // slot + 1 of the record held in r / e
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int x = gx + k;
         const unsigned long long key = keys[py * kTile + px + k];
-        const uint32_t seq1 = (uint32_t)key;
-        if (seq1 == 0) {
-            // Clear (rasterizer.go:36-44) + DotGrid step 10 (:46-52)
-            const bool dot = (x >= 10) && (gy >= 10) && (x % 10 == 0) && (gy % 10 == 0);
-            col[k] = dot ? make_uchar4(100, 100, 100, 255) : make_uchar4(50, 50, 50, 255);
+        const uint32_t slot1 = (uint32_t)key;
+        if (slot1 == 0) {
+            col[k] = background(x, gy);
             zo[k] = -1.0f;
             continue;
         }
-        const uint32_t s = seq1 - 1u;
-        const uint32_t slot = blockBase[s / kSeqStride] + (s % kSeqStride);
-        const TriRec r = load_rec(rec + slot);
-        const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+        const uint32_t slot = slot1 - 1u;
+        if (slot1 != have) {  // neighbouring pixels of a large triangle share the winner
+            r = load_rec(rec + slot);
+            e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+            have = slot1;
+        }
         const int f01 = e.a01 * x + e.b01 * gy + e.c01;
         const int f12 = e.a12 * x + e.b12 * gy + e.c12;
         const int f20 = e.a20 * x + e.b20 * gy + e.c20;
@@ -273,20 +446,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(const __grid_con
                              go_u8(fmul((float)c.z, intensity)), c.w);
         zo[k] = z;
     }
-
-    const size_t pix = ((size_t)frame * a.height + gy) * a.width + gx;
-    if ((a.width & 3) == 0) {
-        // gx is a multiple of 4 and so is width: 16-byte aligned, whole quad in range
-        uint4 cq;
-        cq.x = *reinterpret_cast<uint32_t *>(&col[0]); cq.y = *reinterpret_cast<uint32_t *>(&col[1]);
-        cq.z = *reinterpret_cast<uint32_t *>(&col[2]); cq.w = *reinterpret_cast<uint32_t *>(&col[3]);
-        *reinterpret_cast<uint4 *>(a.color + pix) = cq;
-        *reinterpret_cast<float4 *>(a.depth + pix) = make_float4(zo[0], zo[1], zo[2], zo[3]);
-    } else {
-        for (int k = 0; k < 4 && gx + k < a.width; k++) {
-            a.color[pix + k] = col[k];
-            a.depth[pix + k] = zo[k];
-        }
+    write_quad(a, frame, gx, gy, col, zo);
     }
 }
 

@@ -11,11 +11,15 @@
 //    triangle records plus the device-tile bin counts.
 //
 // One thread per face; a block owns kFaceBlock consecutive faces of one
-// object.  Emitted triangles of a block are written contiguously in
-// submission order (block-level exclusive scan); the block's base slot comes
-// from one atomicAdd, and the submission-order key of a triangle is
-// (faceBlock * kSeqStride + rank in block), which is monotone in
-// (object, face, fan) without any cross-block scan.
+// object and its warps are independent (no block barrier).  The emitted
+// triangles of a warp are compacted with a ballot and stored at statically
+// assigned record slots: slot = object base + warp index * slots-per-warp +
+// rank in warp.  Slot order is submission order (object, face, fan), so the
+// slot doubles as the depth-tie order key of the raster kernel and no scan or
+// atomic is needed to place records.  Binning: the warp groups its triangles
+// by first device tile (match.any) and takes one atomic per group to hand out
+// list positions (stored in the record, so the fill kernel needs no atomics
+// for them); tiles beyond the first are only counted.
 
 #include "gr_types.cuh"
 #include "kernels.h"
@@ -181,7 +185,7 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
     t.w0 = s0.w; t.w1 = s1.w; t.w2 = s2.w;
     t.i0 = i0; t.i1 = i1; t.i2 = i2;
     t.tex = tex;
-    t.seq1 = 0;
+    t.binPos = 0;
 
     // Pixel (x,y) is finally owned by the highest-index reference tile that
     // contains it: column min(x / tw, ntx-1).  A triangle is drawn there iff it
@@ -203,27 +207,36 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
     return e;
 }
 
-// Writes the record and counts it into the device tile bins.
-__device__ __forceinline__ void commit_triangle(const DrawArgs &a, int frame, TriRec rec, const TriUV *uv,
-                                                uint32_t slot, uint32_t seq1) {
-    rec.seq1 = seq1;
+// Device tiles covered by a record's raster bbox.
+struct TileSpan {
+    int tx0, ty0, tx1, ty1;
+    __device__ __forceinline__ int count() const { return (tx1 - tx0 + 1) * (ty1 - ty0 + 1); }
+};
+__device__ __forceinline__ TileSpan tile_span(const TriRec &r) {
+    return {r.bx0 / kTile, r.by0 / kTile, r.bx1 / kTile, r.by1 / kTile};
+}
+
+// Writes the record (4 x 128-bit stores) and its UVs.
+__device__ __forceinline__ void store_record(const DrawArgs &a, int frame, const TriRec &rec, const TriUV &uv,
+                                             uint32_t slot) {
     TriRec *dst = a.rec + (size_t)frame * a.recCap + slot;
     const int4 *s = reinterpret_cast<const int4 *>(&rec);
     int4 *d = reinterpret_cast<int4 *>(dst);
     d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
-    if (rec.tex >= 0) a.uv[(size_t)frame * a.recCap + slot] = *uv;
+    if (rec.tex >= 0) a.uv[(size_t)frame * a.recCap + slot] = uv;
+}
 
-    const int tx0 = rec.bx0 / kTile, tx1 = rec.bx1 / kTile;
-    const int ty0 = rec.by0 / kTile, ty1 = rec.by1 / kTile;
-    const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-    if (n > kMaxBinsPerTri) {
+// Counts the tiles after the first one (B part of the lists) / appends to bigList.
+__device__ __forceinline__ void count_other_tiles(const DrawArgs &a, int frame, const TileSpan &sp, uint32_t slot) {
+    if (sp.count() > kMaxBinsPerTri) {
         const uint32_t pos = atomicAdd(&a.counters[frame].bigCount, 1u);
         a.bigList[(size_t)frame * a.recCap + pos] = slot;
-    } else {
-        uint32_t *cnt = a.tileCount + (size_t)frame * a.ntx * a.nty;
-        for (int ty = ty0; ty <= ty1; ty++)
-            for (int tx = tx0; tx <= tx1; tx++) atomicAdd(&cnt[ty * a.ntx + tx], 1u);
+        return;
     }
+    uint32_t *cntB = a.tileCount + ((size_t)frame * 2 + 1) * a.ntx * a.nty;
+    for (int ty = sp.ty0; ty <= sp.ty1; ty++)
+        for (int tx = sp.tx0; tx <= sp.tx1; tx++)
+            if (ty != sp.ty0 || tx != sp.tx0) atomicAdd(&cntB[ty * a.ntx + tx], 1u);
 }
 
 // renderer.go:328-337: xyz(normalize4(world * n)) . L, with w (=1, translated)
@@ -233,30 +246,6 @@ __device__ __forceinline__ float light_intensity(const float *world, float4 n, f
     const float len = fsqrt(fadd(fadd(fadd(fmul(wn.x, wn.x), fmul(wn.y, wn.y)), fmul(wn.z, wn.z)), fmul(wn.w, wn.w)));
     const float nx = fdiv(wn.x, len), ny = fdiv(wn.y, len), nz = fdiv(wn.z, len);
     return fadd(0.5f, fmul(dot3(nx, ny, nz, lx, ly, lz), 0.5f));
-}
-
-// Exclusive scan of one int per thread over a 256-thread block; returns the
-// thread's offset and the block total.
-__device__ __forceinline__ int block_exclusive_scan(int v, int &total) {
-    __shared__ int warpSum[kFaceBlock / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) warpSum[wid] = inc;
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kFaceBlock / 32; w++) {
-        const int s = warpSum[w];
-        if (w < wid) base += s;
-        tot += s;
-    }
-    total = tot;
-    return base + inc - v;
 }
 
 // ---------------------------------------------------------------- K2
@@ -321,7 +310,13 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
     }
 
     int tpf = 0, nbad = 0;
-    const uint32_t seqBase = (uint32_t)fb * kSeqStride + 1u;
+    const unsigned lane = threadIdx.x & 31u, warpInBlock = threadIdx.x >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const uint32_t warpGlobal = (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock;
+    const uint32_t slot0 = fo.slotBase + ((uint32_t)(fb - ob.faceBlockBase) * kWarpsPerFaceBlock + warpInBlock) *
+                                             (CLIP ? kWarpSlotsClip : kWarpSlots);
+    uint32_t *cntA = a.tileCount + (size_t)frame * 2 * a.ntx * a.nty;
+    uint32_t emitted = 0;  // warp total
 
     if constexpr (!CLIP) {
         Emit e;
@@ -332,20 +327,33 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
             tpf = e.tpf;
             nbad = e.bad ? 1 : 0;
         }
-        int total;
-        const int off = block_exclusive_scan(e.valid ? 1 : 0, total);
-        __shared__ uint32_t sBase;
-        if (threadIdx.x == 0) {
-            sBase = total ? atomicAdd(&a.counters[frame].triCount, (uint32_t)total) : 0u;
-            a.blockBase[(size_t)frame * a.nFaceBlocks + fb] = sBase;
+        const unsigned validMask = __ballot_sync(0xffffffffu, e.valid);
+        emitted = __popc(validMask);
+        if (e.valid) {
+            const uint32_t slot = slot0 + __popc(validMask & ltMask);
+            const TileSpan sp = tile_span(e.rec);
+            const bool big = sp.count() > kMaxBinsPerTri;
+            // one atomic per (warp, first tile): the group leader reserves list positions for its peers
+            const unsigned binMask = __ballot_sync(validMask, !big);
+            if (!big) {
+                const int t0 = sp.ty0 * a.ntx + sp.tx0;
+                const unsigned peers = __match_any_sync(binMask, t0);
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&cntA[t0], (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                e.rec.binPos = base + __popc(peers & ltMask);
+            } else {
+                e.rec.binPos = 0;
+            }
+            store_record(a, frame, e.rec, fuv, slot);
+            if (big || sp.count() > 1) count_other_tiles(a, frame, sp, slot);
         }
-        __syncthreads();
-        if (e.valid) commit_triangle(a, frame, e.rec, &fuv, sBase + off, seqBase + off);
     } else {
         ClipVert poly[9], tmp[9];
         ScreenVert sv[9];
         int count = 0;
-        unsigned validMask = 0;
+        unsigned validBits = 0;
         if (alive) {
             poly[0] = {v0, fuv.u0, fuv.v0, in0};
             poly[1] = {v1, fuv.u1, fuv.v1, in1};
@@ -359,35 +367,42 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
                                               poly[i + 2].in, tex);
                 tpf += e.tpf;
                 nbad += e.bad ? 1 : 0;
-                if (e.valid) validMask |= 1u << i;
+                if (e.valid) validBits |= 1u << i;
             }
         }
-        int total;
-        int off = block_exclusive_scan(__popc(validMask), total);
-        __shared__ uint32_t sBase;
-        if (threadIdx.x == 0) {
-            sBase = total ? atomicAdd(&a.counters[frame].triCount, (uint32_t)total) : 0u;
-            a.blockBase[(size_t)frame * a.nFaceBlocks + fb] = sBase;
+        // exclusive scan of the per-lane triangle counts over the warp
+        const int mine = __popc(validBits);
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((int)lane >= d) inc += t;
         }
-        __syncthreads();
+        emitted = (uint32_t)__shfl_sync(0xffffffffu, inc, 31);
+        uint32_t slot = slot0 + (uint32_t)(inc - mine);
         for (int i = 0; i + 2 < count; i++) {
-            if (!(validMask & (1u << i))) continue;
-            const Emit e = setup_triangle(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in, poly[i + 2].in,
-                                          tex);
+            if (!(validBits & (1u << i))) continue;
+            Emit e = setup_triangle(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in, poly[i + 2].in, tex);
             const TriUV uv = {poly[0].u, poly[0].v, poly[i + 1].u, poly[i + 1].v, poly[i + 2].u, poly[i + 2].v};
-            commit_triangle(a, frame, e.rec, &uv, sBase + off, seqBase + off);
-            off++;
+            const TileSpan sp = tile_span(e.rec);
+            const bool big = sp.count() > kMaxBinsPerTri;
+            e.rec.binPos = big ? 0u : atomicAdd(&cntA[sp.ty0 * a.ntx + sp.tx0], 1u);
+            store_record(a, frame, e.rec, uv, slot);
+            if (big || sp.count() > 1) count_other_tiles(a, frame, sp, slot);
+            slot++;
         }
     }
+    if (lane == 0) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = emitted;
 
     // TPF (renderer.go:436-441) and diagnostics: one atomic per warp
     for (int d = 16; d > 0; d >>= 1) {
         tpf += __shfl_xor_sync(0xffffffffu, tpf, d);
         nbad += __shfl_xor_sync(0xffffffffu, nbad, d);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (tpf) atomicAdd(&a.counters[frame].tpf, (unsigned long long)tpf);
         if (nbad) atomicAdd(&a.counters[frame].outOfDomain, (uint32_t)nbad);
+        if (emitted) atomicAdd(&a.counters[frame].triCount, emitted);
     }
 }
 

@@ -110,7 +110,7 @@ typedef struct grb_triangle_rec {
     float i0, i1, i2;                 /* vertex intensities                */
     int16_t bx0, by0, bx1, by1;       /* inclusive raster bbox after the tile-list rule */
     int32_t tex;                      /* texture id, -1 = face colour      */
-    uint32_t seq1;                    /* submission-order key + 1          */
+    uint32_t bin_pos;                 /* position in its first device tile's list */
 } grb_triangle_rec;
 
 /* Per-frame statistics. */
