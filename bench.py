@@ -120,6 +120,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_summary(kernel: str, frames_per_launch: int):
+    """Per-launch DRAM traffic and issue rates of `kernel` from the newest committed ncu summary
+    (profiles/r*_ncu_c3_batch64.json, written from an `ncu --set full` capture of the same scene and
+    batch size); None when there is no capture for this batch size."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_c3_batch*.json")))
+    if not files:
+        return None
+    d = json.load(open(files[-1]))
+    k = d.get("kernels", {}).get(kernel)
+    if not k or k.get("frames_per_launch") != frames_per_launch:
+        return None
+    k = dict(k)
+    k["file"] = os.path.relpath(files[-1], ROOT)
+    return k
+
+
 def build_scene():
     from gorender_b200 import workloads
 
@@ -313,9 +331,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     dom_bytes = alg[dom] * B
     achieved = dom_bytes / (ktimes[dom] * 1e-3) / 1e9
     path_bytes = 16.0 * nverts + 12.0 * nfaces + 16.0 * nfaces + 8.0 * WIDTH * HEIGHT
+    ncu = ncu_summary(dom, B)
     roofline = {
         "bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / hbm_peak, "traffic": ncu["dram_bytes_total"] if ncu else None, "peak_source": peak_src,
+        "ncu": ({"file": ncu["file"], "issue_active_pct": ncu["issue_active_pct"],
+                 "sm_throughput_pct": ncu["sm_throughput_pct"], "dram_throughput_pct": ncu["dram_throughput_pct"],
+                 "warp_instructions_per_launch": ncu["warp_instructions"],
+                 "note": "the path is instruction-issue bound, not HBM bound: issue slots active vs DRAM % of peak"}
+                if ncu else None),
         "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": ktimes[dom],
         "kernel_ms_per_launch": ktimes, "frames_per_launch": B, "kernel_share": {k: v / max(sum(ktimes.values()), 1e-12) for k, v in ktimes.items()},
         "path_bytes_per_frame": path_bytes, "path_achieved_gbs": path_bytes * fps / world / 1e9,
