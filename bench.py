@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="frames per batched Draw call")
     ap.add_argument("--cpu-sample-frames", type=int, default=400, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="frames", choices=["frames", "strips"],
+                    help="frames: frame-parallel C3 batches (the headline metric); strips: sort-first screen strips "
+                         "of the 2M-triangle 3840x2160 C4 frame gathered to rank 0 over NCCL (strong scaling)")
     return ap.parse_args()
 
 
@@ -196,6 +199,83 @@ def run_reference(args, rank: int):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- sort-first strips (C4)
+
+def run_strips(args, rank: int, world: int, local_rank: int):
+    """BASELINE.json configs[3]: 10 textured Gouraud spheres (2.0 M faces) at 3840x2160, every rank
+    rasterises its tile-aligned row strip, strips are gathered to rank 0 with grouped NCCL
+    send/recv.  Total work is fixed as N grows: strong scaling.  A step = `--strip-frames` frames."""
+    import torch
+    import torch.distributed as dist
+    import gorender_b200 as g
+    from gorender_b200 import parallel, workloads
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W4, H4 = 3840, 2160
+    objs, cam = workloads.config_c4(SPHERE_N)
+    nfaces = sum(len(o.Mesh.Faces) for o in objs)
+    stream = torch.cuda.Stream()
+    dev = g.Device(local_rank, stream.cuda_stream)
+    FR = 4
+    K, Wm = args.steps, args.warmup
+    with torch.cuda.stream(stream):
+        tfb = parallel.TorchFrameBuffer(W4, H4, 1, dev, torch.device("cuda", local_rank))
+        r = g.Renderer(tfb.fb)
+        rots = spin_frames(0, FR)
+        packed = []
+        base_rot = [o.Rotation.copy() for o in objs]
+        for f in range(FR):
+            for o, b in zip(objs, base_rot):  # every instance spins from its own start angle
+                o.Rotation = np.array([b[0], np.float32(b[1] + rots[f]), b[2]], dtype=np.float32)
+            packed.append(np.ascontiguousarray(r.pack_objects(objs, [cam])))
+
+        def one_frame(f):
+            parallel.draw_strip(r, packed[f % FR], H4, world, rank)
+            if world > 1:
+                parallel.gather_strips_to_rank0(tfb.color[0], tfb.depth[0], H4)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            dev.synchronize()
+
+        for s_ in range(Wm):
+            for f in range(FR):
+                one_frame(f)
+        barrier()
+        l0 = dev.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s_ in range(K):
+            for f in range(FR):
+                one_frame(f)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = dev.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    fps = K * FR / (ms * 1e-3)
+    if rank == 0:
+        covered = int((tfb.depth[0] > -1).sum().item())
+        print(json.dumps({
+            "metric": "Mtriangles/s (submitted scene triangles x FPS), 2M-tri scene @3840x2160, sort-first strips",
+            "value": fps * nfaces / 1e6, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "fps": fps, "ms_per_frame": ms / (K * FR), "gpu_launches": int(launches), "covered_pixels": covered,
+            "config": {"workload": "C4: 10 x textured Gouraud 200k-triangle spheres, 3840x2160 (BASELINE.json configs[3])",
+                       "frames_per_step": FR, "parallelism": f"sort-first strips x{world}, NCCL gather to rank 0"},
+        }), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------- this repo's arm
@@ -402,7 +482,10 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-    run_b200(args, rank, world, local_rank)
+    if args.mode == "strips":
+        run_strips(args, rank, world, local_rank)
+    else:
+        run_b200(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
