@@ -91,6 +91,7 @@ SIGNATURES = {
     "grb_context_set_stream": (C.c_int32, [_VP, _VP]),
     "grb_context_synchronize": (C.c_int32, [_VP]),
     "grb_context_set_kernel_timing": (C.c_int32, [_VP, C.c_int32]),
+    "grb_context_set_stage_capture": (C.c_int32, [_VP, C.c_int32]),
     "grb_kernel_times": (C.c_int32, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "grb_launch_count": (C.c_int64, [_VP]),
     "grb_host_alloc": (_VP, [C.c_uint64]),

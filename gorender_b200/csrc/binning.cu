@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kFaceBlock) bin_fill_kernel(const __grid_const
         const int4 q = __ldg(reinterpret_cast<const int4 *>(rec + slot) + 3);
         const int bx0 = (int16_t)(q.x & 0xffff), by0 = (int16_t)(q.x >> 16);
         const int bx1 = (int16_t)(q.y & 0xffff), by1 = (int16_t)(q.y >> 16);
+        if (bx1 < bx0) continue;  // survived the cull but draws nothing (setup.cu)
         const int tx0 = bx0 / kTile, tx1 = bx1 / kTile, ty0 = by0 / kTile, ty1 = by1 / kTile;
         if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kMaxBinsPerTri) continue;  // in bigList
         const int t0 = ty0 * a.ntx + tx0;

@@ -101,6 +101,9 @@ struct grb_context {
     // seam scratch
     DevBuf<float4> seam;
 
+    // also run K1 so that grb_debug_read_transformed has something to read
+    bool stageCapture = false;
+
     // timing
     bool timing = false;
     cudaEvent_t tev[6] = {};
@@ -340,7 +343,8 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     const size_t F = (size_t)nframes;
     // a larger per-frame stride invalidates nothing that is live across draws except the zeroed tile counters
     if (int32_t r = ensure(ctx, ctx->dFrameObjs, nfo, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->tv, F * std::max(ctx->totalVerts, 1), false)) return r;
+    if (ctx->stageCapture)
+        if (int32_t r = ensure(ctx, ctx->tv, F * std::max(ctx->totalVerts, 1), false)) return r;
     if (int32_t r = ensure(ctx, ctx->rec, F * recCap, false)) return r;
     if (int32_t r = ensure(ctx, ctx->uv, F * recCap, false)) return r;
     if (int32_t r = ensure(ctx, ctx->bigList, F * recCap, false)) return r;
@@ -415,7 +419,8 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     }
     const bool tm = ctx->timing;
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[0], s));
-    if (anyVisible) launch_transform(a, nframes, s);
+    // K1 only feeds the stage read-back (grb_debug_read_transformed); K2 transforms on its own
+    if (anyVisible && ctx->stageCapture) launch_transform(a, nframes, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[1], s));
     if (anyVisible) launch_setup(a, nframes, anyPlain, anyClip, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[2], s));
@@ -429,7 +434,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     CK(ctx, cudaEventRecord(fb->drawDone, s));
 
     int launches = 2;  // scan + raster
-    if (anyVisible) launches += 2 + (anyPlain ? 1 : 0) + (anyClip ? 1 : 0);
+    if (anyVisible) launches += 1 + (ctx->stageCapture ? 1 : 0) + (anyPlain ? 1 : 0) + (anyClip ? 1 : 0);
     ctx->totalLaunches += launches;
 
     if (tm) {
@@ -537,6 +542,12 @@ int32_t grb_context_set_kernel_timing(grb_context *ctx, int32_t enable) {
     return GRB_OK;
 }
 
+int32_t grb_context_set_stage_capture(grb_context *ctx, int32_t enable) {
+    if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
+    ctx->stageCapture = enable != 0;
+    return GRB_OK;
+}
+
 int32_t grb_kernel_times(grb_context *ctx, double out_ms[5], int64_t *out_launches) {
     if (!ctx || !out_ms) return fail(ctx, GRB_ERR_INVALID, "null argument");
     for (int k = 0; k < 5; k++) { out_ms[k] = ctx->accMs[k]; ctx->accMs[k] = 0; }
@@ -634,6 +645,22 @@ int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_i
     m.dev.uvs = f2;
     if ((r = upload(ctx, d->tex, d->nf, &i32, m.allocs))) goto bad;
     m.dev.tex = i32;
+    {   // face-corner expansion (gr_types.cuh): corner k of face f at cv[k][f]
+        std::vector<float4> corner(d->nf);
+        const float4 *hv = reinterpret_cast<const float4 *>(d->vertices);
+        const float4 *hn = reinterpret_cast<const float4 *>(d->vnormals);
+        for (int k = 0; k < 3; k++) {
+            for (int32_t f = 0; f < d->nf; f++) corner[f] = hv[d->vidx[3 * f + k]];
+            if ((r = upload(ctx, corner.data(), d->nf, &f4, m.allocs))) goto bad;
+            m.dev.cv[k] = f4;
+            m.dev.cn[k] = nullptr;
+            if (d->nvn > 0) {
+                for (int32_t f = 0; f < d->nf; f++) corner[f] = hn[d->nidx[3 * f + k]];
+                if ((r = upload(ctx, corner.data(), d->nf, &f4, m.allocs))) goto bad;
+                m.dev.cn[k] = f4;
+            }
+        }
+    }
     ctx->meshes.push_back(std::move(m));
     ctx->meshesDirty = true;
     ctx->planValid = false;
@@ -797,6 +824,7 @@ int32_t grb_matrix_multiply_vec4_batch(grb_context *ctx, const float m[16], floa
 
 int32_t grb_debug_read_transformed(grb_context *ctx, int32_t frame, float *out, int64_t capacity_vec4, int64_t *out_n) {
     if (!ctx || frame < 0 || frame >= ctx->lastFrames) return fail(ctx, GRB_ERR_INVALID, "no such frame in the last draw");
+    if (!ctx->stageCapture) return fail(ctx, GRB_ERR_STATE, "enable grb_context_set_stage_capture before the draw");
     if (int32_t r = set_device(ctx)) return r;
     const int64_t n = ctx->totalVerts;
     if (out_n) *out_n = n;
@@ -829,25 +857,33 @@ int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_r
     if (nobj) CK(ctx, cudaMemcpy(fo.data(), ctx->dFrameObjs.p + (size_t)frame * nobj, nobj * sizeof(FrameObj), cudaMemcpyDeviceToHost));
     const bool optClip = ctx->lastOptions & GRB_OPT_FRUSTUM_CLIPPING;
     int64_t k = 0;
-    for (int32_t i = 0; i < nobj && k < n; i++) {
+    std::vector<grb_triangle_rec> seg;
+    std::vector<TriUV> seguv;
+    for (int32_t i = 0; i < nobj; i++) {
         if (fo[i].visibility == GRB_BOX_OUTSIDE) continue;
         const bool clips = optClip && fo[i].visibility != GRB_BOX_INSIDE;
         const uint32_t perWarp = clips ? kWarpSlotsClip : kWarpSlots;
         const DrawObj &ob = ctx->planObjs[i];
         const int32_t nf = ctx->meshes[ob.mesh].dev.nf;
         const int32_t blocks = (nf + kFaceBlock - 1) / kFaceBlock;
-        for (int64_t w = 0; w < (int64_t)blocks * kWarpsPerFaceBlock && k < n; w++) {
+        for (int64_t w = 0; w < (int64_t)blocks * kWarpsPerFaceBlock; w++) {
             const uint32_t cnt = wc[(size_t)ob.faceBlockBase * kWarpsPerFaceBlock + w];
             if (cnt == 0) continue;
-            if (k + cnt > n) return fail(ctx, GRB_ERR_STATE, "record walk disagrees with the triangle counter");
             const size_t slot = (size_t)frame * ctx->recCap + fo[i].slotBase + (size_t)w * perWarp;
-            CK(ctx, cudaMemcpy(out + k, ctx->rec.p + slot, cnt * sizeof(TriRec), cudaMemcpyDeviceToHost));
-            if (out_uvs) {
-                CK(ctx, cudaMemcpy(out_uvs + 6 * k, ctx->uv.p + slot, cnt * sizeof(TriUV), cudaMemcpyDeviceToHost));
-                for (uint32_t j = 0; j < cnt; j++)
-                    if (out[k + j].tex < 0) std::memset(out_uvs + 6 * (k + j), 0, 24);
+            seg.resize(cnt);
+            seguv.resize(cnt);
+            CK(ctx, cudaMemcpy(seg.data(), ctx->rec.p + slot, cnt * sizeof(TriRec), cudaMemcpyDeviceToHost));
+            CK(ctx, cudaMemcpy(seguv.data(), ctx->uv.p + slot, cnt * sizeof(TriUV), cudaMemcpyDeviceToHost));
+            for (uint32_t j = 0; j < cnt; j++) {
+                if (seg[j].bx1 < seg[j].bx0) continue;  // slot of a face that survived the cull but draws nothing
+                if (k >= n) return fail(ctx, GRB_ERR_STATE, "record walk disagrees with the triangle counter");
+                out[k] = seg[j];
+                if (out_uvs) {
+                    if (seg[j].tex >= 0) std::memcpy(out_uvs + 6 * k, &seguv[j], 24);
+                    else std::memset(out_uvs + 6 * k, 0, 24);
+                }
+                k++;
             }
-            k += cnt;
         }
     }
     if (k != n) return fail(ctx, GRB_ERR_STATE, "record walk disagrees with the triangle counter");

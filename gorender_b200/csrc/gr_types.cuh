@@ -4,7 +4,7 @@
 // TexDev).  Everything a draw produces lives in a per-context workspace,
 // struct-of-arrays over the frames of a batch:
 //
-//   tv        [frames][totalVerts]        float4   clip-space vertices        (K1 -> K2)
+//   tv        [frames][totalVerts]        float4   clip-space vertices (K1; only when stage capture is on)
 //   rec       [frames][recCap]            TriRec   emitted triangles, 64 B    (K2 -> K4,K5)
 //   uv        [frames][recCap]            TriUV    24 B, textured faces only  (K2 -> K5)
 //   warpCount [frames][nFaceBlocks*8]     u32      triangles emitted by a warp (K2 -> K4)
@@ -39,6 +39,11 @@ struct MeshDev {
     const float4 *verts;
     const float4 *vnormals;
     const float4 *fnormals;
+    // Face-corner expansion built once at upload: corner k of face f at cv[k][f] (object space)
+    // and, for meshes with vertex normals, cn[k][f].  The per-frame kernels stream these with
+    // fully coalesced 128-bit loads instead of gathering through the index arrays.
+    const float4 *cv[3];
+    const float4 *cn[3];
     const int32_t *vidx;     // 3 per face
     const int32_t *nidx;     // 3 per face
     const float2 *uvs;       // 3 per face

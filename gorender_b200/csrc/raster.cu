@@ -422,7 +422,9 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
         const int f20 = e.a20 * x + e.b20 * gy + e.c20;
         float al, be, ga;
         barycentric(f01, f12, f20, al, be, ga);
-        const float z = z_reciprocal(al, be, ga, r.w0, r.w1, r.w2);
+        // zRec of the winner is in the key, bit for bit (phase A computed it with the same
+        // operations): no need to redo the three divides of rasterizer.go:153
+        const float z = from_orderable((uint32_t)(key >> 32));
         // rasterizer.go:162
         const float intensity = fadd(fadd(fmul(al, r.i0), fmul(be, r.i1)), fmul(ga, r.i2));
         uchar4 c = make_uchar4(200, 200, 200, 255);  // faceColor (renderer.go:17)

@@ -2,7 +2,9 @@
 //
 // K1 replaces matrixMultiplyVec4Batch on the vertex array
 //    (renderer.go:303-304; asm_amd64.s:22-47): one thread per vertex,
-//    128-bit load, 16 separately rounded FMUL + 12 FADD, 128-bit store.
+//    128-bit load, 16 separately rounded FMUL + 12 FADD, 128-bit store.  It backs the
+//    build-tag seam (grb_matrix_multiply_vec4_batch) and the stage read-back of
+//    Object.TransformedVertices; the frame path fuses the same transform into K2.
 // K2 replaces the per-face loop of projectObject (renderer.go:315-396):
 //    gather, backface cull (:246-250), lighting (:326-346), Sutherland–Hodgman
 //    frustum clip (clipping.go:167-236), perspective divide + viewport
@@ -124,13 +126,29 @@ struct ScreenVert {
     float sx, sy, w;
 };
 
-// renderer.go:365-370: p / p.w (4 true divides), full screen-matrix rows, W restored
+// renderer.go:365-370: p / p.w (4 true divides), full screen-matrix rows, W restored.
+// Two of the four divides are skipped when their result provably cannot change sx, sy:
+//   * w / w is exactly 1 for every finite non-zero w;
+//   * z / w only enters as (0 * qz): the screen matrix has m[0][2] = m[1][2] = 0
+//     (matrix.go:108-118), so for a finite quotient the term is +-0 and x + (+-0) == x in every
+//     later comparison and in the integer snap.  |z| <= 2^60 and |w| >= 2^-60 keep the quotient
+//     finite; anything else (and any other screen matrix) takes the literal path.
 __device__ __forceinline__ ScreenVert to_screen(const Mat4 &S, float4 p) {
-    const float4 q = make_float4(fdiv(p.x, p.w), fdiv(p.y, p.w), fdiv(p.z, p.w), fdiv(p.w, p.w));
     ScreenVert s;
+    s.w = p.w;
+    const float aw = fabsf(p.w);
+    const bool fast = S.m[2] == 0.0f && S.m[6] == 0.0f && aw >= 8.673617e-19f && aw <= 1.1529215e18f &&
+                      fabsf(p.z) <= 1.1529215e18f;
+    if (fast) {
+        const float qx = fdiv(p.x, p.w), qy = fdiv(p.y, p.w);
+        // ((m0*qx + m1*qy) + m2*qz) + m3*1 with the m2*qz = +-0 term dropped
+        s.sx = fadd(fadd(fmul(S.m[0], qx), fmul(S.m[1], qy)), S.m[3]);
+        s.sy = fadd(fadd(fmul(S.m[4], qx), fmul(S.m[5], qy)), S.m[7]);
+        return s;
+    }
+    const float4 q = make_float4(fdiv(p.x, p.w), fdiv(p.y, p.w), fdiv(p.z, p.w), fdiv(p.w, p.w));
     s.sx = mat_row(S.m, q);
     s.sy = mat_row(S.m + 4, q);
-    s.w = p.w;
     return s;
 }
 
@@ -157,8 +175,14 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
     e.tpf = 0;
 
     // identifyTriangleTiles (renderer.go:226-244) on the float screen points
-    const float minX = gomin(gomin(s0.sx, s1.sx), s2.sx), maxX = gomax(gomax(s0.sx, s1.sx), s2.sx);
-    const float minY = gomin(gomin(s0.sy, s1.sy), s2.sy), maxY = gomax(gomax(s0.sy, s1.sy), s2.sy);
+    // Go's min/max propagate NaN (then every tile comparison below is false): one check up front
+    // instead of one per operation
+    const float nanSum = fadd(fadd(fadd(s0.sx, s1.sx), fadd(s2.sx, s0.sy)), fadd(s1.sy, s2.sy));
+    if (nanSum != nanSum && (s0.sx != s0.sx || s1.sx != s1.sx || s2.sx != s2.sx || s0.sy != s0.sy || s1.sy != s1.sy ||
+                             s2.sy != s2.sy))
+        return e;  // in no tile list: tpf 0, no record
+    const float minX = fminf(fminf(s0.sx, s1.sx), s2.sx), maxX = fmaxf(fmaxf(s0.sx, s1.sx), s2.sx);
+    const float minY = fminf(fminf(s0.sy, s1.sy), s2.sy), maxY = fmaxf(fmaxf(s0.sy, s1.sy), s2.sy);
     const float Wf = (float)a.width, Hf = (float)a.height;
     int c0 = 1 << 30, c1 = -1, r0 = 1 << 30, r1 = -1, nc = 0, nr = 0;
     for (int c = 0; c < a.ref.ntx; c++) {   // calculateTileBoundaries (renderer.go:50-76)
@@ -250,6 +274,11 @@ __device__ __forceinline__ float light_intensity(const float *world, float4 n, f
 
 // ---------------------------------------------------------------- K2
 
+// Face data handed from the cull phase to the emit phase of a block through shared memory.
+struct __align__(16) StagedFace {
+    float4 v0, v1, v2;       // clip-space vertices
+};
+
 template <bool CLIP>
 __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant__ DrawArgs a) {
     const int frame = blockIdx.y;
@@ -264,17 +293,21 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
     if (objClips != CLIP) return;  // the other instantiation owns this block
 
     const MeshDev &m = a.meshes[ob.mesh];
-    const int f = (fb - ob.faceBlockBase) * kFaceBlock + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, warpInBlock = threadIdx.x >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    uint32_t *cntA = a.tileCount + (size_t)frame * 2 * a.ntx * a.nty;
 
+    // ------------------------------------------------------------ phase 1: transform + cull
+    // The MVP transform of the face's three corners (matrixMultiplyVec4Batch, renderer.go:303-304,
+    // asm_amd64.s:22-47) is fused here: corners stream in coalesced from the upload-time
+    // face-corner expansion, so there is no clip-space vertex array to write and gather back.
+    int f = (fb - ob.faceBlockBase) * kFaceBlock + threadIdx.x;
     bool alive = f < m.nf;
     float4 v0, v1, v2;
-    float in0 = 0.5f, in1 = 0.5f, in2 = 0.5f;  // ambientStrength (renderer.go:342-346)
-    int tex = -1;
-
     if (alive) {
-        const float4 *tv = a.tv + (size_t)frame * a.totalVerts + ob.vertBase;
-        const int i0 = __ldg(&m.vidx[3 * f]), i1 = __ldg(&m.vidx[3 * f + 1]), i2 = __ldg(&m.vidx[3 * f + 2]);
-        v0 = tv[i0]; v1 = tv[i1]; v2 = tv[i2];
+        v0 = mat_vec(fo.mvp, __ldg(&m.cv[0][f]));
+        v1 = mat_vec(fo.mvp, __ldg(&m.cv[1][f]));
+        v2 = mat_vec(fo.mvp, __ldg(&m.cv[2][f]));
         if (a.options & GRB_OPT_BACKFACE_CULLING) {
             // facingCamera (renderer.go:246-250) on clip-space xyz
             const float e1x = fsub(v1.x, v0.x), e1y = fsub(v1.y, v0.y), e1z = fsub(v1.z, v0.z);
@@ -287,13 +320,57 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
         }
     }
 
+    uint32_t slot;  // record slot(s) of this thread's face: static, in submission order
+    if constexpr (!CLIP) {
+        // Surviving faces (40 % of C3's) are compacted across the block so that the expensive part
+        // below — 12 IEEE divides, a square root, the tile tests, the record stores — runs in
+        // full warps; warps left without work retire here.
+        __shared__ StagedFace staged[kFaceBlock];
+        __shared__ uint32_t stagedMeta[kFaceBlock][2];   // face index, record slot
+        __shared__ uint32_t warpAlive[kWarpsPerFaceBlock];
+        const unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
+        const uint32_t warpGlobal = (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock;
+        const uint32_t slot0 = fo.slotBase + ((uint32_t)(fb - ob.faceBlockBase) * kWarpsPerFaceBlock + warpInBlock) * kWarpSlots;
+        if (lane == 0) {
+            warpAlive[warpInBlock] = __popc(aliveMask);
+            // slots [slot0, slot0 + count) are in use; the ones whose triangle turns out to be
+            // invisible are marked with an empty bbox in phase 2
+            a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = __popc(aliveMask);
+        }
+        __syncthreads();
+        uint32_t base = 0, nAlive = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerFaceBlock; w++) {
+            const uint32_t c = warpAlive[w];
+            if (w < (int)warpInBlock) base += c;
+            nAlive += c;
+        }
+        if (alive) {
+            const uint32_t rank = __popc(aliveMask & ltMask);
+            staged[base + rank] = {v0, v1, v2};
+            stagedMeta[base + rank][0] = (uint32_t)f;
+            stagedMeta[base + rank][1] = slot0 + rank;
+        }
+        __syncthreads();
+        alive = threadIdx.x < nAlive;
+        if (warpInBlock * 32 >= nAlive) return;  // whole warp idle
+        if (alive) {
+            const StagedFace sf = staged[threadIdx.x];
+            v0 = sf.v0; v1 = sf.v1; v2 = sf.v2;
+            f = (int)stagedMeta[threadIdx.x][0];
+            slot = stagedMeta[threadIdx.x][1];
+        }
+    }
+
+    // ------------------------------------------------------------ phase 2: light, project, emit
+    float in0 = 0.5f, in1 = 0.5f, in2 = 0.5f;  // ambientStrength (renderer.go:342-346)
+    int tex = -1;
     if (alive) {
         if (a.options & GRB_OPT_LIGHTING) {
             if (m.nvn != 0 && !(a.options & GRB_OPT_FLAT_SHADING)) {
-                const int n0 = __ldg(&m.nidx[3 * f]), n1 = __ldg(&m.nidx[3 * f + 1]), n2 = __ldg(&m.nidx[3 * f + 2]);
-                in0 = light_intensity(fo.world, __ldg(&m.vnormals[n0]), a.lx, a.ly, a.lz);
-                in1 = light_intensity(fo.world, __ldg(&m.vnormals[n1]), a.lx, a.ly, a.lz);
-                in2 = light_intensity(fo.world, __ldg(&m.vnormals[n2]), a.lx, a.ly, a.lz);
+                in0 = light_intensity(fo.world, __ldg(&m.cn[0][f]), a.lx, a.ly, a.lz);
+                in1 = light_intensity(fo.world, __ldg(&m.cn[1][f]), a.lx, a.ly, a.lz);
+                in2 = light_intensity(fo.world, __ldg(&m.cn[2][f]), a.lx, a.ly, a.lz);
             } else {
                 in0 = in1 = in2 = light_intensity(fo.world, __ldg(&m.fnormals[f]), a.lx, a.ly, a.lz);
             }
@@ -310,13 +387,7 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
     }
 
     int tpf = 0, nbad = 0;
-    const unsigned lane = threadIdx.x & 31u, warpInBlock = threadIdx.x >> 5;
-    const unsigned ltMask = (1u << lane) - 1u;
-    const uint32_t warpGlobal = (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock;
-    const uint32_t slot0 = fo.slotBase + ((uint32_t)(fb - ob.faceBlockBase) * kWarpsPerFaceBlock + warpInBlock) *
-                                             (CLIP ? kWarpSlotsClip : kWarpSlots);
-    uint32_t *cntA = a.tileCount + (size_t)frame * 2 * a.ntx * a.nty;
-    uint32_t emitted = 0;  // warp total
+    uint32_t emitted = 0;  // warp total of records written
 
     if constexpr (!CLIP) {
         Emit e;
@@ -330,7 +401,6 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
         const unsigned validMask = __ballot_sync(0xffffffffu, e.valid);
         emitted = __popc(validMask);
         if (e.valid) {
-            const uint32_t slot = slot0 + __popc(validMask & ltMask);
             const TileSpan sp = tile_span(e.rec);
             const bool big = sp.count() > kMaxBinsPerTri;
             // one atomic per (warp, first tile): the group leader reserves list positions for its peers
@@ -348,8 +418,15 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
             }
             store_record(a, frame, e.rec, fuv, slot);
             if (big || sp.count() > 1) count_other_tiles(a, frame, sp, slot);
+        } else if (alive) {
+            // survived the cull but draws nothing (off screen / ShowFaces off / out of domain):
+            // leave an empty bbox in its slot so that the fill kernel skips it
+            int4 q = make_int4(1, 0, -1, 0);  // bx0 = 1, by0 = 0, bx1 = 0, by1 = 0
+            reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot)[3] = q;
         }
     } else {
+        const uint32_t warpGlobal = (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock;
+        const uint32_t slot0 = fo.slotBase + ((uint32_t)(fb - ob.faceBlockBase) * kWarpsPerFaceBlock + warpInBlock) * kWarpSlotsClip;
         ClipVert poly[9], tmp[9];
         ScreenVert sv[9];
         int count = 0;
@@ -379,7 +456,7 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
             if ((int)lane >= d) inc += t;
         }
         emitted = (uint32_t)__shfl_sync(0xffffffffu, inc, 31);
-        uint32_t slot = slot0 + (uint32_t)(inc - mine);
+        slot = slot0 + (uint32_t)(inc - mine);
         for (int i = 0; i + 2 < count; i++) {
             if (!(validBits & (1u << i))) continue;
             Emit e = setup_triangle(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in, poly[i + 2].in, tex);
@@ -391,8 +468,8 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
             if (big || sp.count() > 1) count_other_tiles(a, frame, sp, slot);
             slot++;
         }
+        if (lane == 0) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = emitted;
     }
-    if (lane == 0) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = emitted;
 
     // TPF (renderer.go:436-441) and diagnostics: one atomic per warp
     for (int d = 16; d > 0; d >>= 1) {

@@ -66,6 +66,10 @@ class Device:
     def set_kernel_timing(self, enable: bool) -> None:
         self.check(self.lib.grb_context_set_kernel_timing(self.h, int(bool(enable))))
 
+    def set_stage_capture(self, enable: bool) -> None:
+        """Also run the standalone transform kernel so `Renderer.debug_transformed` has data."""
+        self.check(self.lib.grb_context_set_stage_capture(self.h, int(bool(enable))))
+
     def kernel_times(self):
         ms = (C.c_double * 5)()
         n = C.c_int64()

@@ -137,6 +137,10 @@ int32_t grb_context_synchronize(grb_context *ctx);
 /* When enabled, every draw records CUDA events between its kernels and
  * accumulates per-kernel time (ms) retrievable with grb_kernel_times. */
 int32_t grb_context_set_kernel_timing(grb_context *ctx, int32_t enable);
+/* When enabled, draws also run the standalone per-vertex transform kernel and keep its output
+ * (Object.TransformedVertices, mesh.go:76) for grb_debug_read_transformed.  Off by default: the
+ * frame path fuses the transform into the setup kernel and never materialises that array. */
+int32_t grb_context_set_stage_capture(grb_context *ctx, int32_t enable);
 /* out_ms[0..4] = transform, setup, bin-scan, bin-fill, raster; out_launches =
  * number of kernel launches accumulated.  Resets the accumulators. */
 int32_t grb_kernel_times(grb_context *ctx, double out_ms[5], int64_t *out_launches);

@@ -87,13 +87,17 @@ def test_matrix_multiply_vec4_batch_seam(device, oracle):
 def test_stage_parity(name, device, oracle):
     """Stage-wise: BoxVisibility, clip-space vertices, emitted triangles (snap, w, intensity, uv, texture)."""
     sc = scene_defs.PINNED[name]()
-    fb, r = render(sc, device)
+    device.set_stage_capture(True)   # also run the standalone transform kernel and keep its output
+    try:
+        fb, r = render(sc, device)
+        tv = r.debug_transformed(0)
+    finally:
+        device.set_stage_capture(False)
     ref = oracle.draw(r, sc.objects, sc.camera, record=True)
     vis = r.debug_visibility(0, len(sc.objects))
     assert vis.tolist() == ref["visibility"].tolist()
 
     # Object.TransformedVertices of every visible object
-    tv = r.debug_transformed(0)
     base = 0
     persp = r.perspective()
     for o, v in zip(sc.objects, vis):
