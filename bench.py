@@ -400,17 +400,18 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # ---- roofline: algorithmic bytes per frame of each kernel
     tris = float(stats["triangles"].mean())
     hbm_peak, peak_src = peaks()
-    alg = {
-        "transform": 32.0 * nverts,                                # read 16 B + write 16 B per vertex
-        "setup": 12.0 * nfaces + 16.0 * nverts + 16.0 * tris + 64.0 * tris,   # indices, clip verts, face normals, records
-        "bin_scan": 8.0 * ((WIDTH + 31) // 32) * ((HEIGHT + 31) // 32),
-        "bin_fill": 16.0 * tris + 4.0 * tris,                      # bbox quarter of the record + list entry
-        "raster": 8.0 * WIDTH * HEIGHT + 64.0 * tris + 4.0 * tris,  # colour + depth out, records + list in
+    ntiles = ((WIDTH + 31) // 32) * ((HEIGHT + 31) // 32)
+    alg = {   # algorithmic bytes per frame of each kernel
+        "transform": 0.0,                                          # fused into setup (stage capture only)
+        "setup": 48.0 * nfaces + 16.0 * tris + 64.0 * tris + 8.0 * tris / 6.0,   # corners in; normals, records, descriptors
+        "bin_scan": 0.0, "bin_fill": 0.0,                          # no such kernels any more
+        "raster": 8.0 * WIDTH * HEIGHT + 64.0 * tris + 8.0 * tris / 6.0 + 4.0 * ntiles,  # fb out; records, descriptors, counters in
     }
+    ktimes = {k: v for k, v in ktimes.items() if alg.get(k, 0.0) > 0.0}
     dom = max(ktimes, key=lambda k: ktimes[k])
     dom_bytes = alg[dom] * B
     achieved = dom_bytes / (ktimes[dom] * 1e-3) / 1e9
-    path_bytes = 16.0 * nverts + 12.0 * nfaces + 16.0 * nfaces + 8.0 * WIDTH * HEIGHT   # SURVEY.md §8d, C3
+    path_bytes = 16.0 * nverts + 12.0 * nfaces + 16.0 * nfaces + 8.0 * WIDTH * HEIGHT   # SURVEY.md section 8d, C3
     ncu = ncu_summary(dom, B)
     roofline = {
         "bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

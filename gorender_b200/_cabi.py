@@ -58,7 +58,7 @@ class grb_triangle_rec(C.Structure):
         ("w0", C.c_float), ("w1", C.c_float), ("w2", C.c_float),
         ("i0", C.c_float), ("i1", C.c_float), ("i2", C.c_float),
         ("bx0", C.c_int16), ("by0", C.c_int16), ("bx1", C.c_int16), ("by1", C.c_int16),
-        ("tex", C.c_int32), ("bin_pos", C.c_uint32),
+        ("tex", C.c_int32), ("order", C.c_uint32),
     ]
 
 
@@ -74,7 +74,7 @@ TRIANGLE_DTYPE = np.dtype([
     ("w0", np.float32), ("w1", np.float32), ("w2", np.float32),
     ("i0", np.float32), ("i1", np.float32), ("i2", np.float32),
     ("bx0", np.int16), ("by0", np.int16), ("bx1", np.int16), ("by1", np.int16),
-    ("tex", np.int32), ("bin_pos", np.uint32)])
+    ("tex", np.int32), ("order", np.uint32)])
 STATS_DTYPE = np.dtype([("tpf", np.int64), ("triangles", np.int32), ("big_triangles", np.int32),
                         ("out_of_domain", np.int32), ("reserved", np.int32)])
 assert OBJECT_DTYPE.itemsize == C.sizeof(grb_object) == 132

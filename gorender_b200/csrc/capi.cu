@@ -89,7 +89,9 @@ struct grb_context {
     DevBuf<float4> tv;
     DevBuf<TriRec> rec;
     DevBuf<TriUV> uv;
-    DevBuf<uint32_t> warpCount, tileCount, tileOff, tileOffB, cursor, binList, bigList;
+    DevBuf<uint32_t> warpCount, descCount, bigList;
+    DevBuf<TileDesc> desc;
+    DevBuf<OverflowDesc> overflow;
     DevBuf<FrameCounters> counters;
     uint32_t recCap = 0;  // per frame
 
@@ -348,18 +350,18 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     if (int32_t r = ensure(ctx, ctx->rec, F * recCap, false)) return r;
     if (int32_t r = ensure(ctx, ctx->uv, F * recCap, false)) return r;
     if (int32_t r = ensure(ctx, ctx->bigList, F * recCap, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->binList, F * recCap * kMaxBinsPerTri, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->warpCount, F * std::max(ctx->nFaceBlocks, 1) * kWarpsPerFaceBlock, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->tileOff, F * (nTiles + 1), false)) return r;
-    if (int32_t r = ensure(ctx, ctx->tileOffB, F * nTiles, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->cursor, F * nTiles, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->overflow, F * recCap * kMaxBinsPerTri, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->desc, F * nTiles * kDescCap, false)) return r;
+    if (ctx->stageCapture)
+        if (int32_t r = ensure(ctx, ctx->warpCount, F * std::max(ctx->nFaceBlocks, 1) * kWarpsPerFaceBlock, false)) return r;
     if (int32_t r = ensure(ctx, ctx->counters, F, false)) return r;
     ctx->recCap = recCap;
-    // tile counters must be zero on entry; K3 re-zeroes what K2 counted, but the
-    // per-frame stride depends on nTiles, so clear when the geometry changes
-    if (ctx->tileCount.cap < F * 2 * nTiles || ctx->lastNTiles != nTiles) {
-        if (int32_t r = ensure(ctx, ctx->tileCount, F * 2 * nTiles, false)) return r;
-        CK(ctx, cudaMemsetAsync(ctx->tileCount.p, 0, ctx->tileCount.cap * sizeof(uint32_t), ctx->stream));
+    // per-tile descriptor counters must be zero on entry; the raster kernel re-zeroes what it
+    // consumed, but the per-frame stride depends on nTiles (and a strip draw leaves the other
+    // rows' tiles untouched, at zero), so clear only when the geometry changes
+    if (ctx->descCount.cap < F * nTiles || ctx->lastNTiles != nTiles) {
+        if (int32_t r = ensure(ctx, ctx->descCount, F * nTiles, false)) return r;
+        CK(ctx, cudaMemsetAsync(ctx->descCount.p, 0, ctx->descCount.cap * sizeof(uint32_t), ctx->stream));
     }
 
     CK(ctx, cudaMemcpyAsync(ctx->dFrameObjs.p, hfo, nfo * sizeof(FrameObj), cudaMemcpyHostToDevice, ctx->stream));
@@ -381,12 +383,11 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.tv = ctx->tv.p;
     a.rec = ctx->rec.p;
     a.uv = ctx->uv.p;
-    a.warpCount = ctx->warpCount.p;
-    a.tileCount = ctx->tileCount.p;
-    a.tileOff = ctx->tileOff.p;
-    a.tileOffB = ctx->tileOffB.p;
-    a.cursor = ctx->cursor.p;
-    a.binList = ctx->binList.p;
+    a.warpCount = ctx->stageCapture ? ctx->warpCount.p : nullptr;
+    a.descCount = ctx->descCount.p;
+    a.desc = ctx->desc.p;
+    a.overflow = ctx->overflow.p;
+    a.descCap = kDescCap;
     a.bigList = ctx->bigList.p;
     a.counters = ctx->counters.p;
     a.recCap = recCap;
@@ -424,17 +425,17 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[1], s));
     if (anyVisible) launch_setup(a, nframes, anyPlain, anyClip, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[2], s));
-    launch_bin_scan(a, nframes, s);
+    // (slots 2 and 3 of the timing array were the separate bin-scan / bin-fill kernels; binning
+    // now happens inside the setup kernel)
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[3], s));
-    if (anyVisible) launch_bin_fill(a, nframes, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[4], s));
     launch_raster(a, nframes, s);
     if (tm) CK(ctx, cudaEventRecord(ctx->tev[5], s));
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaEventRecord(fb->drawDone, s));
 
-    int launches = 2;  // scan + raster
-    if (anyVisible) launches += 1 + (ctx->stageCapture ? 1 : 0) + (anyPlain ? 1 : 0) + (anyClip ? 1 : 0);
+    int launches = 1;  // raster
+    if (anyVisible) launches += (ctx->stageCapture ? 1 : 0) + (anyPlain ? 1 : 0) + (anyClip ? 1 : 0);
     ctx->totalLaunches += launches;
 
     if (tm) {
@@ -504,8 +505,8 @@ int32_t grb_context_destroy(grb_context *ctx) {
     for (auto &t : ctx->textures)
         if (t.pixels) cudaFree(t.pixels);
     void *bufs[] = {ctx->dMeshes.p, ctx->dTextures.p, ctx->dObjs.p, ctx->dVblk.p, ctx->dFblk.p, ctx->dFrameObjs.p,
-                    ctx->tv.p, ctx->rec.p, ctx->uv.p, ctx->warpCount.p, ctx->tileCount.p, ctx->tileOff.p, ctx->tileOffB.p,
-                    ctx->cursor.p, ctx->binList.p, ctx->bigList.p, ctx->counters.p, ctx->seam.p};
+                    ctx->tv.p, ctx->rec.p, ctx->uv.p, ctx->warpCount.p, ctx->descCount.p, ctx->desc.p, ctx->overflow.p,
+                    ctx->bigList.p, ctx->counters.p, ctx->seam.p};
     for (void *p : bufs)
         if (p) cudaFree(p);
     for (int i = 0; i < kStagingRing; i++) {
@@ -838,6 +839,7 @@ int32_t grb_debug_read_transformed(grb_context *ctx, int32_t frame, float *out, 
 int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_rec *out, float *out_uvs,
                                  int64_t capacity, int64_t *out_n) {
     if (!ctx || frame < 0 || frame >= ctx->lastFrames) return fail(ctx, GRB_ERR_INVALID, "no such frame in the last draw");
+    if (!ctx->stageCapture) return fail(ctx, GRB_ERR_STATE, "enable grb_context_set_stage_capture before the draw");
     if (int32_t r = set_device(ctx)) return r;
     FrameCounters c;
     CK(ctx, cudaMemcpyAsync(&c, ctx->counters.p + frame, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));

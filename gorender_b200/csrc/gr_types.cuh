@@ -5,15 +5,12 @@
 // struct-of-arrays over the frames of a batch:
 //
 //   tv        [frames][totalVerts]        float4   clip-space vertices (K1; only when stage capture is on)
-//   rec       [frames][recCap]            TriRec   emitted triangles, 64 B    (K2 -> K4,K5)
+//   rec       [frames][recCap]            TriRec   emitted triangles, 64 B    (K2 -> K5)
 //   uv        [frames][recCap]            TriUV    24 B, textured faces only  (K2 -> K5)
-//   warpCount [frames][nFaceBlocks*8]     u32      triangles emitted by a warp (K2 -> K4)
-//   tileCount [frames][2][nTiles]         u32      A: first-tile entries (positions handed out
-//                                                  in K2), B: other tiles   (K2 -> K3; K3 re-zeroes)
-//   tileOff   [frames][nTiles+1]          u32      list start per tile       (K3 -> K4,K5)
-//   tileOffB  [frames][nTiles]            u32      start of the B part       (K3 -> K4)
-//   cursor    [frames][nTiles]            u32      B-part cursor (K3 zeroes -> K4)
-//   binList   [frames][kMaxBinsPerTri*recCap] u32  rec slots per tile         (K4 -> K5)
+//   warpCount [frames][nFaceBlocks*8]     u32      slots used per warp (stage capture only)
+//   descCount [frames][nTiles]            u32      descriptors appended per tile (K2 -> K5; K5 re-zeroes)
+//   desc      [frames][nTiles][descCap]   TileDesc per-tile triangle lists, 8 B per (warp, tile) group
+//   overflow  [frames][kMaxBinsPerTri*recCap] OverflowDesc  descriptors beyond descCap (rare)
 //   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles
 //   counters  [frames]                    FrameCounters
 #pragma once
@@ -33,6 +30,7 @@ constexpr int kWarpSlots = 32;             // rec slots reserved per warp, objec
 constexpr int kWarpSlotsClip = 256;        // ... objects that clip (<= 7 triangles per face)
 constexpr int kMaxFan = 7;                 // clipping.go:10: <= 9 vertices -> <= 7 triangles
 constexpr int kMaxBinsPerTri = 16;         // more tiles than this -> bigList
+constexpr int kDescCap = 512;              // descriptors a tile holds in place; the rest go to `overflow`
 constexpr int kCoordLimit = 16383;         // |snapped coord| bound of the int32 edge-function domain
 
 struct MeshDev {
@@ -83,7 +81,17 @@ struct __align__(16) TriRec {   // == grb_triangle_rec, 64 B
     float w2, i0, i1, i2;
     int16_t bx0, by0, bx1, by1;
     int32_t tex;
-    uint32_t binPos;         // position in the list of the triangle's first device tile
+    uint32_t order;          // the record's slot == submission-order key
+};
+
+// One entry of a tile's triangle list: the record slots base + {set bits of mask}.  A warp of
+// the setup kernel appends one per (32-slot segment, tile) group, so a list entry stands for ~8
+// triangles of C3 and costs one atomic.
+struct __align__(8) TileDesc {
+    uint32_t base, mask;
+};
+struct __align__(16) OverflowDesc {
+    uint32_t tile, base, mask, pad;
 };
 static_assert(sizeof(TriRec) == 64, "TriRec must be 64 bytes");
 static_assert(sizeof(grb_triangle_rec) == 64, "ABI record must be 64 bytes");
@@ -96,7 +104,7 @@ struct __align__(16) FrameCounters {
     uint32_t triCount;
     uint32_t bigCount;
     uint32_t outOfDomain;
-    uint32_t pad;
+    uint32_t overflowCount;
     unsigned long long tpf;
     unsigned long long pad2;
 };
@@ -121,12 +129,11 @@ struct DrawArgs {
     float4 *tv;
     TriRec *rec;
     TriUV *uv;
-    uint32_t *warpCount;
-    uint32_t *tileCount;
-    uint32_t *tileOff;
-    uint32_t *tileOffB;
-    uint32_t *cursor;
-    uint32_t *binList;
+    uint32_t *warpCount;        // null unless stage capture is on
+    uint32_t *descCount;
+    TileDesc *desc;
+    OverflowDesc *overflow;
+    uint32_t descCap;
     uint32_t *bigList;
     FrameCounters *counters;
     uint32_t recCap;

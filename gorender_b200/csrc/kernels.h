@@ -1,4 +1,4 @@
-// kernels.h — host-callable launchers of the five per-draw kernels.
+// kernels.h — host-callable launchers of the per-draw kernels.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -7,15 +7,11 @@
 
 namespace gr {
 
-// K1: clip-space vertices of every visible object of every frame.
+// K1: clip-space vertices of every visible object of every frame (stage capture / seam only).
 void launch_transform(const DrawArgs &a, int nframes, cudaStream_t s);
-// K2: cull / light / clip / project / snap / emit + tile counts.
+// K2: transform / cull / light / clip / project / snap / emit records + per-tile descriptor lists.
 void launch_setup(const DrawArgs &a, int nframes, bool anyPlain, bool anyClip, cudaStream_t s);
-// K3: exclusive scan of the per-tile counts (one block per frame).
-void launch_bin_scan(const DrawArgs &a, int nframes, cudaStream_t s);
-// K4: scatter triangle slots into the per-tile lists.
-void launch_bin_fill(const DrawArgs &a, int nframes, cudaStream_t s);
-// K5: per-tile coverage + z resolve in shared memory, shade, coalesced write-back.
+// K3: per-tile coverage + z resolve in shared memory, shade, coalesced write-back.
 void launch_raster(const DrawArgs &a, int nframes, cudaStream_t s);
 // matrixMultiplyVec4Batch over a device array.
 void launch_matvec_batch(const float m[16], float4 *vecs, long long n, cudaStream_t s);

@@ -11,9 +11,10 @@
 // (rasterizer.go:156): later triangles win ties, so the surviving fragment of
 // a pixel is the lexicographic maximum of (zRec, submission order) — which is
 // exactly max(key), in any processing order.  Phase A resolves coverage and
-// depth for all triangles of the tile in parallel (small triangles: one
-// thread each, shared-memory atomic max; large triangles: the whole block,
-// each thread owning four pixels, no atomics).  Phase B shades only the
+// depth for all triangles of the tile in parallel, each warp working through
+// its share of the tile's descriptor list without block barriers (small
+// triangles: warp-wide coarse / fine stages; large ones: the warp sweeps the
+// tile rows; always a shared-memory atomic max on the key).  Phase B shades only the
 // winning fragment of each pixel (perspective-correct UV, Gouraud intensity,
 // nearest texel through the read-only path), generates the cleared
 // background and dot grid for uncovered pixels, and writes colour and depth
@@ -128,6 +129,8 @@ struct WarpTris {            // one per warp, 32 triangles
     uint32_t box[32];        // local x0 | local y0 << 5 | (bw-1) << 10
 };
 constexpr int kFragRing = 64;
+constexpr int kLargeQueue = 1024;  // large triangles a block queues per round before falling back to warp sweeps
+constexpr int kDescRound = 256;    // descriptors expanded per round (one per thread)
 
 // fine stage for `count` (<= 32) queued fragments starting at ring position `head`
 __device__ __forceinline__ void fine_stage(const WarpTris &wt, const uint32_t *ring, uint32_t head, int count, int lane,
@@ -183,27 +186,175 @@ __device__ __forceinline__ void write_quad(const DrawArgs &a, int frame, int gx,
     }
 }
 
-// Large triangle staged in shared memory for the cooperative pass: edge functions set up once
-// by the thread that queued it.
-struct __align__(16) CoopTri {
-    int a01, b01, c01, a12;
-    int b12, c12, a20, b20;
-    int c20;
-    float w0, w1, w2;
-    int16_t bx0, by0, bx1, by1;
-    uint32_t slot;
-    uint32_t pad;
-};
-static_assert(sizeof(CoopTri) == 64, "CoopTri must be 64 bytes");
+// One batch of up to 32 list entries of a warp: lane `lane` holds record slot `slot` when
+// `have`.  Small triangles go through the coarse / fine stages; a large one (more than kSmallArea
+// pixels inside the tile) is swept by the whole warp, one tile row at a time, lane = column.
+__device__ __forceinline__ void process_batch(bool have, uint32_t slot, const TriRec *rec, WarpTris &wt, uint32_t *ring,
+                                              uint32_t &qHead, uint32_t &qTail, int lane, int tileX, int tileY,
+                                              int tileX1, int tileY1, unsigned long long *keys, uint32_t *largeQ,
+                                              int *largeCount) {
+    const unsigned ltMask = (1u << lane) - 1u;
+    int area = 0;
+    bool large = false;
+    if (have) {
+        const TriRec r = load_rec(rec + slot);
+        const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
+        const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
+        if (x0 <= x1 && y0 <= y1) {
+            const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
+            if (n <= kSmallArea) {
+                const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+                wt.a01[lane] = e.a01; wt.b01[lane] = e.b01; wt.c01[lane] = e.c01;
+                wt.a12[lane] = e.a12; wt.b12[lane] = e.b12; wt.c12[lane] = e.c12;
+                wt.a20[lane] = e.a20; wt.b20[lane] = e.b20; wt.c20[lane] = e.c20;
+                wt.w0[lane] = r.w0; wt.w1[lane] = r.w1; wt.w2[lane] = r.w2;
+                wt.slot[lane] = slot;
+                wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)(bw - 1) << 10);
+                area = n;
+            } else {
+                large = true;
+            }
+        }
+    }
+    // ---- small triangles: flatten the 32 bboxes into one pixel list
+    int incl = area;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - area;
+    __syncwarp();
+    for (int item0 = 0; item0 < total; item0 += 32) {
+        const int item = min(item0 + lane, total - 1);
+        // triangle owning this pixel: number of lanes whose inclusive sum is <= item
+        int t = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, t + step - 1);
+            if (v <= item) t += step;
+        }
+        const int j = item - __shfl_sync(0xffffffffu, excl, t);
+        const uint32_t box = wt.box[t];
+        const int bw = (int)((box >> 10) & 31u) + 1;
+        // j / bw for j < 32: (j + 0.5) / bw is never within 1/64 of an integer
+        const int row = (int)(((float)j + 0.5f) * __frcp_rn((float)bw));
+        const int lx = (int)(box & 31u) + (j - row * bw), ly = (int)((box >> 5) & 31u) + row;
+        const int x = tileX + lx, y = tileY + ly;
+        const int f01 = wt.a01[t] * x + wt.b01[t] * y + wt.c01[t];
+        const int f12 = wt.a12[t] * x + wt.b12[t] * y + wt.c12[t];
+        const int f20 = wt.a20[t] * x + wt.b20[t] * y + wt.c20[t];
+        const bool inside = (item0 + lane < total) && ((f01 & f12 & f20) < 0);
+        const unsigned m = __ballot_sync(0xffffffffu, inside);
+        if (inside) ring[(qTail + __popc(m & ltMask)) & (kFragRing - 1)] = ((uint32_t)t << 10) | ((uint32_t)ly << 5) | (uint32_t)lx;
+        qTail += __popc(m);
+        __syncwarp();
+        if (qTail - qHead >= 32) {
+            fine_stage(wt, ring, qHead, 32, lane, tileX, tileY, keys);
+            qHead += 32;
+        }
+    }
+    // the table is rewritten by the next batch: drain what is left
+    if (qTail != qHead) {
+        fine_stage(wt, ring, qHead, (int)(qTail - qHead), lane, tileX, tileY, keys);
+        qHead = qTail;
+    }
+    __syncwarp();
+
+    // ---- large triangles of the batch are queued for the block-wide pass (thread-owned pixels,
+    // no atomics); if the queue is full the warp sweeps the tile rows itself, lane = column
+    if (large) {
+        const int pos = atomicAdd(largeCount, 1);
+        if (pos < kLargeQueue) {
+            largeQ[pos] = slot;
+            large = false;
+        }
+    }
+    unsigned largeMask = __ballot_sync(0xffffffffu, large);
+    while (largeMask) {
+        const int src = __ffs(largeMask) - 1;
+        largeMask &= largeMask - 1;
+        const uint32_t s = __shfl_sync(0xffffffffu, slot, src);
+        const TriRec r = load_rec(rec + s);  // same address for every lane: one broadcast transaction
+        const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+        const int x = tileX + lane;
+        const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
+        const bool col = x >= r.bx0 && x <= r.bx1 && x <= tileX1;
+        int f01 = e.a01 * x + e.b01 * y0 + e.c01;
+        int f12 = e.a12 * x + e.b12 * y0 + e.c12;
+        int f20 = e.a20 * x + e.b20 * y0 + e.c20;
+        for (int y = y0; y <= y1; y++) {
+            if (col && (f01 & f12 & f20) < 0) {
+                float al, be, ga;
+                barycentric(f01, f12, f20, al, be, ga);
+                const float z = z_reciprocal(al, be, ga, r.w0, r.w1, r.w2);
+                if (z >= -1.0f) {
+                    const unsigned long long key = fragment_key(z, s);
+                    unsigned long long *p = &keys[(y - tileY) * kTile + lane];
+                    if (key > *(volatile unsigned long long *)p) atomicMax(p, key);
+                }
+            }
+            f01 += e.b01; f12 += e.b12; f20 += e.b20;
+        }
+    }
+}
+
+// n-th (0-based) set bit of mask
+__device__ __forceinline__ int nth_set_bit(uint32_t mask, int n) { return __fns(mask, 0, n + 1); }
+
+// Block-wide pass over the queued large triangles: every thread owns 4 consecutive pixels of the
+// tile and keeps their keys in registers while it walks the queue; no atomics.
+__device__ __forceinline__ void coop_pass(const uint32_t *largeQ, int nq, const TriRec *rec, int gx, int gy, int px, int py,
+                                          unsigned long long *keys) {
+    unsigned long long k0 = keys[py * kTile + px], k1 = keys[py * kTile + px + 1];
+    unsigned long long k2 = keys[py * kTile + px + 2], k3 = keys[py * kTile + px + 3];
+    // bbox first (one 16-byte broadcast load): most threads are outside a medium triangle; the
+    // next entry's bbox is fetched one iteration ahead
+    int4 bNext = __ldg(reinterpret_cast<const int4 *>(rec + largeQ[0]) + 3);
+    for (int q = 0; q < nq; q++) {
+        const uint32_t slot = largeQ[q];
+        const int4 b = bNext;
+        if (q + 1 < nq) bNext = __ldg(reinterpret_cast<const int4 *>(rec + largeQ[q + 1]) + 3);
+        const int bx0 = (int16_t)(b.x & 0xffff), by0 = (int16_t)(b.x >> 16);
+        const int bx1 = (int16_t)(b.y & 0xffff), by1 = (int16_t)(b.y >> 16);
+        if (gy < by0 || gy > by1 || gx > bx1 || gx + 3 < bx0) continue;
+        const TriRec r = load_rec(rec + slot);
+        const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+        int f01 = e.a01 * gx + e.b01 * gy + e.c01;
+        int f12 = e.a12 * gx + e.b12 * gy + e.c12;
+        int f20 = e.a20 * gx + e.b20 * gy + e.c20;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = gx + k;
+            if ((f01 & f12 & f20) < 0 && x >= bx0 && x <= bx1) {
+                float al, be, ga;
+                barycentric(f01, f12, f20, al, be, ga);
+                const float z = z_reciprocal(al, be, ga, r.w0, r.w1, r.w2);
+                if (z >= -1.0f) {
+                    const unsigned long long key = fragment_key(z, slot);
+                    if (k == 0) k0 = max(k0, key);
+                    if (k == 1) k1 = max(k1, key);
+                    if (k == 2) k2 = max(k2, key);
+                    if (k == 3) k3 = max(k3, key);
+                }
+            }
+            f01 += e.a01; f12 += e.a12; f20 += e.a20;
+        }
+    }
+    keys[py * kTile + px] = k0; keys[py * kTile + px + 1] = k1;
+    keys[py * kTile + px + 2] = k2; keys[py * kTile + px + 3] = k3;
+}
 
 __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_kernel(const __grid_constant__ DrawArgs a) {
     __shared__ unsigned long long keys[kTilePix];
-    // pass 1 (small triangles) and pass 2 (large ones) never overlap: their tables share storage
-    __shared__ __align__(16) unsigned char scratch[sizeof(CoopTri) * kRasterThreads];
+    __shared__ WarpTris tris[kRasterThreads / 32];
     __shared__ uint32_t fragRing[kRasterThreads / 32][kFragRing];
-    __shared__ int queueCount;
-    static_assert(sizeof(WarpTris) * (kRasterThreads / 32) <= sizeof(scratch), "scratch too small");
-    CoopTri *queue = reinterpret_cast<CoopTri *>(scratch);
+    __shared__ TileDesc dList[kDescRound];
+    __shared__ uint32_t dStart[kDescRound + 1];
+    __shared__ uint32_t warpSums[kRasterThreads / 32];
+    __shared__ uint32_t largeQ[kLargeQueue];
+    __shared__ int largeCount;
 
     const int tid = threadIdx.x;
     const int nTiles = a.ntx * a.nty;
@@ -215,15 +366,31 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     const int tile = ty * a.ntx + tx;
     const int tileX = tx * kTile, tileY = ty * kTile;
 
-    const uint32_t *off = a.tileOff + (size_t)frame * (nTiles + 1);
-    const uint32_t listBegin = off[tile], nList = off[tile + 1] - listBegin;
+    uint32_t *descCount = a.descCount + (size_t)frame * nTiles + tile;
+    const uint32_t nDescAll = *descCount;
     const uint32_t nBig = a.counters[frame].bigCount;
+    const uint32_t nOverflow = nDescAll > a.descCap ? a.counters[frame].overflowCount : 0u;
 
     const int gx = tileX + px, gy = tileY + py;
     const bool inImage = gy < a.height && gx < a.width;
 
-    // ---- nothing touches this tile: cleared background straight to HBM (block-uniform branch)
-    if (nList == 0 && nBig == 0) {
+    // ---- no list entries: unless one of the frame's big triangles reaches this tile, nothing
+    // touches it (block-uniform decision)
+    bool empty = nDescAll == 0;
+    if (empty && nBig != 0) {
+        const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
+        const TriRec *rec = a.rec + (size_t)frame * a.recCap;
+        bool hit = false;
+        for (uint32_t i = tid; i < nBig; i += kRasterThreads) {
+            const int4 b = __ldg(reinterpret_cast<const int4 *>(rec + big[i]) + 3);
+            const int bx0 = (int16_t)(b.x & 0xffff), by0 = (int16_t)(b.x >> 16);
+            const int bx1 = (int16_t)(b.y & 0xffff), by1 = (int16_t)(b.y >> 16);
+            hit |= bx0 < tileX + kTile && bx1 >= tileX && by0 < tileY + kTile && by1 >= tileY;
+        }
+        empty = !__syncthreads_or(hit);
+    }
+    // ---- cleared background straight to HBM
+    if (empty) {
         if (inImage) {
             uchar4 col[4];
             float zo[4];
@@ -239,158 +406,105 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
 
     const int tileX1 = min(tileX + kTile, a.width) - 1, tileY1 = min(tileY + kTile, a.height) - 1;
     const TriRec *rec = a.rec + (size_t)frame * a.recCap;
-    const uint32_t *list = a.binList + (size_t)frame * a.recCap * kMaxBinsPerTri + listBegin;
-    const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
+    const TileDesc *desc = a.desc + ((size_t)frame * nTiles + tile) * a.descCap;
+    const uint32_t nDesc = min(nDescAll, a.descCap);
 
     for (int i = tid; i < kTilePix; i += kRasterThreads) keys[i] = kBackgroundKey;
-    if (tid == 0) queueCount = 0;
     __syncthreads();
+    if (tid == 0) *descCount = 0;  // ready for the next draw (nobody else reads this tile's counter)
 
-    // ------------------------------------------------------------ phase A, pass 1
-    // small triangles, one thread each, no barriers; large ones are only counted
-    int nLarge = 0;
+    // ------------------------------------------------------------ phase A: coverage + depth
     {
         const int lane = tid & 31, warp = tid >> 5;
-        const unsigned ltMask = (1u << lane) - 1u;
-        WarpTris &wt = reinterpret_cast<WarpTris *>(scratch)[warp];
+        constexpr int kWarps = kRasterThreads / 32;
+        WarpTris &wt = tris[warp];
         uint32_t *ring = fragRing[warp];
         uint32_t qHead = 0, qTail = 0;  // warp-uniform
-        for (uint32_t base = warp * 32; base < nList; base += kRasterThreads) {
-            const uint32_t i = base + lane;
-            int area = 0;
-            if (i < nList) {
-                const uint32_t slot = list[i];
-                const TriRec r = load_rec(rec + slot);
-                const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
-                const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
-                if (x0 <= x1 && y0 <= y1) {
-                    const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
-                    if (n <= kSmallArea) {
-                        const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
-                        wt.a01[lane] = e.a01; wt.b01[lane] = e.b01; wt.c01[lane] = e.c01;
-                        wt.a12[lane] = e.a12; wt.b12[lane] = e.b12; wt.c12[lane] = e.c12;
-                        wt.a20[lane] = e.a20; wt.b20[lane] = e.b20; wt.c20[lane] = e.c20;
-                        wt.w0[lane] = r.w0; wt.w1[lane] = r.w1; wt.w2[lane] = r.w2;
-                        wt.slot[lane] = slot;
-                        wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)(bw - 1) << 10);
-                        area = n;
-                    } else {
-                        nLarge++;
-                    }
+        const OverflowDesc *ov = a.overflow + (size_t)frame * a.recCap * kMaxBinsPerTri;
+        const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
+        // Rounds of up to 256 descriptors: first the tile's in-place list, then (rarely) the frame's
+        // overflow list filtered by tile, finally the frame's big list as pseudo-descriptors.
+        const uint32_t nRoundsOwn = (nDesc + kDescRound - 1) / kDescRound;
+        const uint32_t nRoundsOv = (nOverflow + kDescRound - 1) / kDescRound;
+        const uint32_t nRoundsBig = (nBig + kDescRound - 1) / kDescRound;
+        for (uint32_t round = 0; round < nRoundsOwn + nRoundsOv + nRoundsBig; round++) {
+            // -- one descriptor per thread
+            TileDesc d = {0u, 0u};
+            if (round < nRoundsOwn) {
+                const uint32_t i = round * kDescRound + tid;
+                if (i < nDesc) d = desc[i];
+            } else if (round < nRoundsOwn + nRoundsOv) {
+                const uint32_t i = (round - nRoundsOwn) * kDescRound + tid;
+                if (i < nOverflow) {
+                    const OverflowDesc o = ov[i];
+                    if ((int)o.tile == tile) d = {o.base, o.mask};
                 }
-            }
-            // flatten the 32 bboxes into one pixel list
-            int incl = area;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            const int excl = incl - area;
-            __syncwarp();
-            for (int item0 = 0; item0 < total; item0 += 32) {
-                const int item = min(item0 + lane, total - 1);
-                // triangle owning this pixel: number of lanes whose inclusive sum is <= item
-                int t = 0;
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const int v = __shfl_sync(0xffffffffu, incl, t + step - 1);
-                    if (v <= item) t += step;
-                }
-                const int j = item - __shfl_sync(0xffffffffu, excl, t);
-                const uint32_t box = wt.box[t];
-                const int bw = (int)((box >> 10) & 31u) + 1;
-                // j / bw for j < 32: (j + 0.5) / bw is never within 1/64 of an integer
-                const int row = (int)(((float)j + 0.5f) * __frcp_rn((float)bw));
-                const int lx = (int)(box & 31u) + (j - row * bw), ly = (int)((box >> 5) & 31u) + row;
-                const int x = tileX + lx, y = tileY + ly;
-                const int f01 = wt.a01[t] * x + wt.b01[t] * y + wt.c01[t];
-                const int f12 = wt.a12[t] * x + wt.b12[t] * y + wt.c12[t];
-                const int f20 = wt.a20[t] * x + wt.b20[t] * y + wt.c20[t];
-                const bool inside = (item0 + lane < total) && ((f01 & f12 & f20) < 0);
-                const unsigned m = __ballot_sync(0xffffffffu, inside);
-                if (inside) ring[(qTail + __popc(m & ltMask)) & (kFragRing - 1)] = ((uint32_t)t << 10) | ((uint32_t)ly << 5) | (uint32_t)lx;
-                qTail += __popc(m);
-                __syncwarp();
-                if (qTail - qHead >= 32) {
-                    fine_stage(wt, ring, qHead, 32, lane, tileX, tileY, keys);
-                    qHead += 32;
-                }
-            }
-            // the table is rewritten by the next batch: drain what is left
-            if (qTail != qHead) {
-                fine_stage(wt, ring, qHead, (int)(qTail - qHead), lane, tileX, tileY, keys);
-                qHead = qTail;
-            }
-            __syncwarp();
-        }
-    }
-    const int anyLarge = __syncthreads_or(nLarge != 0 || nBig != 0);
-
-    // ------------------------------------------------------------ phase A, pass 2
-    // large triangles (and the big list): the whole block, thread-owned pixels, no atomics
-    if (anyLarge) {
-        const uint32_t nWork = nList + nBig;
-        for (uint32_t base = 0; base < nWork; base += kRasterThreads) {
-            const uint32_t i = base + tid;
-            if (i < nWork) {
-                const uint32_t slot = i < nList ? list[i] : big[i - nList];
-                const int4 q = __ldg(reinterpret_cast<const int4 *>(rec + slot) + 3);
-                const int bx0 = (int16_t)(q.x & 0xffff), by0 = (int16_t)(q.x >> 16);
-                const int bx1 = (int16_t)(q.y & 0xffff), by1 = (int16_t)(q.y >> 16);
-                const int x0 = max(bx0, tileX), x1 = min(bx1, tileX1);
-                const int y0 = max(by0, tileY), y1 = min(by1, tileY1);
-                // list entries with a small footprint were done in pass 1; big-list entries are all done here
-                if (x0 <= x1 && y0 <= y1 && (i >= nList || (x1 - x0 + 1) * (y1 - y0 + 1) > kSmallArea)) {
-                    const TriRec r = load_rec(rec + slot);
-                    const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
-                    CoopTri c;
-                    c.a01 = e.a01; c.b01 = e.b01; c.c01 = e.c01;
-                    c.a12 = e.a12; c.b12 = e.b12; c.c12 = e.c12;
-                    c.a20 = e.a20; c.b20 = e.b20; c.c20 = e.c20;
-                    c.w0 = r.w0; c.w1 = r.w1; c.w2 = r.w2;
-                    c.bx0 = (int16_t)x0; c.by0 = (int16_t)y0; c.bx1 = (int16_t)x1; c.by1 = (int16_t)y1;
-                    c.slot = slot;
-                    c.pad = 0;
-                    queue[atomicAdd(&queueCount, 1)] = c;
-                }
-            }
-            __syncthreads();
-            const int nq = queueCount;
-            if (nq) {
-                unsigned long long k0 = keys[py * kTile + px], k1 = keys[py * kTile + px + 1];
-                unsigned long long k2 = keys[py * kTile + px + 2], k3 = keys[py * kTile + px + 3];
-                for (int q = 0; q < nq; q++) {
-                    const CoopTri c = queue[q];  // same address for every thread: broadcast
-                    if (gy < c.by0 || gy > c.by1 || gx > c.bx1 || gx + 3 < c.bx0) continue;
-                    int f01 = c.a01 * gx + c.b01 * gy + c.c01;
-                    int f12 = c.a12 * gx + c.b12 * gy + c.c12;
-                    int f20 = c.a20 * gx + c.b20 * gy + c.c20;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int x = gx + k;
-                        if ((f01 & f12 & f20) < 0 && x >= c.bx0 && x <= c.bx1) {
-                            float al, be, ga;
-                            barycentric(f01, f12, f20, al, be, ga);
-                            const float z = z_reciprocal(al, be, ga, c.w0, c.w1, c.w2);
-                            if (z >= -1.0f) {
-                                const unsigned long long key = fragment_key(z, c.slot);
-                                if (k == 0) k0 = max(k0, key);
-                                if (k == 1) k1 = max(k1, key);
-                                if (k == 2) k2 = max(k2, key);
-                                if (k == 3) k3 = max(k3, key);
-                            }
-                        }
-                        f01 += c.a01; f12 += c.a12; f20 += c.a20;
-                    }
-                }
-                keys[py * kTile + px] = k0; keys[py * kTile + px + 1] = k1;
-                keys[py * kTile + px + 2] = k2; keys[py * kTile + px + 3] = k3;
+            } else {
+                // big-list entries skip the expansion: whatever overlaps the tile goes straight to
+                // the block-wide pass (256 entries per round never overflow the queue)
+                if (tid == 0) largeCount = 0;
                 __syncthreads();
-                if (tid == 0) queueCount = 0;
+                const uint32_t i = (round - nRoundsOwn - nRoundsOv) * kDescRound + tid;
+                if (i < nBig) {
+                    const uint32_t slot = big[i];
+                    const int4 b = __ldg(reinterpret_cast<const int4 *>(rec + slot) + 3);
+                    const int bx0 = (int16_t)(b.x & 0xffff), by0 = (int16_t)(b.x >> 16);
+                    const int bx1 = (int16_t)(b.y & 0xffff), by1 = (int16_t)(b.y >> 16);
+                    if (bx0 <= tileX1 && bx1 >= tileX && by0 <= tileY1 && by1 >= tileY) largeQ[atomicAdd(&largeCount, 1)] = slot;
+                }
+                __syncthreads();
+                const int nqBig = largeCount;
+                if (nqBig) coop_pass(largeQ, nqBig, rec, gx, gy, px, py, keys);
+                __syncthreads();
+                continue;
+            }
+            // -- block-wide exclusive scan of the triangle counts: entry e belongs to the descriptor
+            //    with dStart[i] <= e < dStart[i+1], so entries can be dealt to the warps evenly
+            const uint32_t cnt = __popc(d.mask);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int s_ = 1; s_ < 32; s_ <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, s_);
+                if (lane >= s_) incl += v;
+            }
+            if (lane == 31) warpSums[warp] = incl;
+            if (tid == 0) largeCount = 0;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) {
+                const uint32_t v = warpSums[w];
+                if (w < warp) wbase += v;
+                total += v;
+            }
+            dList[tid] = d;
+            dStart[tid] = wbase + incl - cnt;
+            if (tid == 0) dStart[kDescRound] = total;
+            __syncthreads();
+            // -- batches of 32 entries, round-robin over the warps
+            const uint32_t nBatches = (total + 31) / 32;
+            for (uint32_t b = warp; b < nBatches; b += kWarps) {
+                const uint32_t e = b * 32 + lane;
+                const bool have = e < total;
+                uint32_t slot = 0;
+                if (have) {
+                    int lo = 0;  // largest i with dStart[i] <= e
+#pragma unroll
+                    for (int step = kDescRound / 2; step >= 1; step >>= 1)
+                        if (dStart[lo + step] <= e) lo += step;
+                    const TileDesc dd = dList[lo];
+                    slot = dd.base + (uint32_t)__fns(dd.mask, 0, (int)(e - dStart[lo]) + 1);
+                }
+                process_batch(have, slot, rec, wt, ring, qHead, qTail, lane, tileX, tileY, tileX1, tileY1, keys, largeQ,
+                              &largeCount);
             }
             __syncthreads();
+            // -- large triangles found in this round
+            const int nq = min(largeCount, kLargeQueue);
+            if (nq) {
+                coop_pass(largeQ, nq, rec, gx, gy, px, py, keys);
+                __syncthreads();
+            }
         }
     }
 

@@ -18,10 +18,12 @@
 // assigned record slots: slot = object base + warp index * slots-per-warp +
 // rank in warp.  Slot order is submission order (object, face, fan), so the
 // slot doubles as the depth-tie order key of the raster kernel and no scan or
-// atomic is needed to place records.  Binning: the warp groups its triangles
-// by first device tile (match.any) and takes one atomic per group to hand out
-// list positions (stored in the record, so the fill kernel needs no atomics
-// for them); tiles beyond the first are only counted.
+// atomic is needed to place records.  Binning happens here too: the warp
+// groups its triangles by (first device tile, 32-slot record segment) with
+// match.any and appends ONE 8-byte descriptor {segment base, bit mask} per
+// group to the tile's list — one atomic per ~8 triangles, no separate count /
+// scan / fill passes.  Triangles straddling tile borders add single-triangle
+// descriptors to their other tiles.
 
 #include "gr_types.cuh"
 #include "kernels.h"
@@ -209,7 +211,7 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
     t.w0 = s0.w; t.w1 = s1.w; t.w2 = s2.w;
     t.i0 = i0; t.i1 = i1; t.i2 = i2;
     t.tex = tex;
-    t.binPos = 0;
+    t.order = 0;
 
     // Pixel (x,y) is finally owned by the highest-index reference tile that
     // contains it: column min(x / tw, ntx-1).  A triangle is drawn there iff it
@@ -250,17 +252,30 @@ __device__ __forceinline__ void store_record(const DrawArgs &a, int frame, const
     if (rec.tex >= 0) a.uv[(size_t)frame * a.recCap + slot] = uv;
 }
 
-// Counts the tiles after the first one (B part of the lists) / appends to bigList.
-__device__ __forceinline__ void count_other_tiles(const DrawArgs &a, int frame, const TileSpan &sp, uint32_t slot) {
+// Appends one descriptor to a tile's list (or to the overflow list when the tile's in-place
+// segment is full).
+__device__ __forceinline__ void append_desc(const DrawArgs &a, int frame, int tile, uint32_t base, uint32_t mask) {
+    const int nTiles = a.ntx * a.nty;
+    const uint32_t pos = atomicAdd(&a.descCount[(size_t)frame * nTiles + tile], 1u);
+    if (pos < a.descCap) {
+        a.desc[((size_t)frame * nTiles + tile) * a.descCap + pos] = {base, mask};
+    } else {
+        const uint32_t o = atomicAdd(&a.counters[frame].overflowCount, 1u);
+        a.overflow[(size_t)frame * a.recCap * kMaxBinsPerTri + o] = {(uint32_t)tile, base, mask, 0u};
+    }
+}
+
+// The tiles after a triangle's first one get single-triangle descriptors; triangles spanning
+// more than kMaxBinsPerTri tiles go to the frame's big list, which every tile scans.
+__device__ __forceinline__ void bin_other_tiles(const DrawArgs &a, int frame, const TileSpan &sp, uint32_t slot) {
     if (sp.count() > kMaxBinsPerTri) {
         const uint32_t pos = atomicAdd(&a.counters[frame].bigCount, 1u);
         a.bigList[(size_t)frame * a.recCap + pos] = slot;
         return;
     }
-    uint32_t *cntB = a.tileCount + ((size_t)frame * 2 + 1) * a.ntx * a.nty;
     for (int ty = sp.ty0; ty <= sp.ty1; ty++)
         for (int tx = sp.tx0; tx <= sp.tx1; tx++)
-            if (ty != sp.ty0 || tx != sp.tx0) atomicAdd(&cntB[ty * a.ntx + tx], 1u);
+            if (ty != sp.ty0 || tx != sp.tx0) append_desc(a, frame, ty * a.ntx + tx, slot & ~31u, 1u << (slot & 31u));
 }
 
 // renderer.go:328-337: xyz(normalize4(world * n)) . L, with w (=1, translated)
@@ -295,7 +310,6 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
     const MeshDev &m = a.meshes[ob.mesh];
     const unsigned lane = threadIdx.x & 31u, warpInBlock = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
-    uint32_t *cntA = a.tileCount + (size_t)frame * 2 * a.ntx * a.nty;
 
     // ------------------------------------------------------------ phase 1: transform + cull
     // The MVP transform of the face's three corners (matrixMultiplyVec4Batch, renderer.go:303-304,
@@ -334,8 +348,8 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
         if (lane == 0) {
             warpAlive[warpInBlock] = __popc(aliveMask);
             // slots [slot0, slot0 + count) are in use; the ones whose triangle turns out to be
-            // invisible are marked with an empty bbox in phase 2
-            a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = __popc(aliveMask);
+            // invisible are marked with an empty bbox in phase 2 (only the stage read-back looks)
+            if (a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = __popc(aliveMask);
         }
         __syncthreads();
         uint32_t base = 0, nAlive = 0;
@@ -403,24 +417,21 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
         if (e.valid) {
             const TileSpan sp = tile_span(e.rec);
             const bool big = sp.count() > kMaxBinsPerTri;
-            // one atomic per (warp, first tile): the group leader reserves list positions for its peers
+            e.rec.order = slot;
+            store_record(a, frame, e.rec, fuv, slot);
+            // one descriptor (one atomic) per (first tile, 32-slot segment) group of the warp
             const unsigned binMask = __ballot_sync(validMask, !big);
             if (!big) {
                 const int t0 = sp.ty0 * a.ntx + sp.tx0;
-                const unsigned peers = __match_any_sync(binMask, t0);
-                const int leader = __ffs(peers) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(&cntA[t0], (uint32_t)__popc(peers));
-                base = __shfl_sync(peers, base, leader);
-                e.rec.binPos = base + __popc(peers & ltMask);
-            } else {
-                e.rec.binPos = 0;
+                const unsigned long long groupKey = ((unsigned long long)(uint32_t)t0 << 32) | (slot & ~31u);
+                const unsigned peers = __match_any_sync(binMask, groupKey);
+                const uint32_t groupMask = __reduce_or_sync(peers, 1u << (slot & 31u));
+                if ((int)lane == __ffs(peers) - 1) append_desc(a, frame, t0, slot & ~31u, groupMask);
             }
-            store_record(a, frame, e.rec, fuv, slot);
-            if (big || sp.count() > 1) count_other_tiles(a, frame, sp, slot);
-        } else if (alive) {
+            if (big || sp.count() > 1) bin_other_tiles(a, frame, sp, slot);
+        } else if (alive && a.warpCount) {
             // survived the cull but draws nothing (off screen / ShowFaces off / out of domain):
-            // leave an empty bbox in its slot so that the fill kernel skips it
+            // leave an empty bbox in its slot so that the stage read-back skips it
             int4 q = make_int4(1, 0, -1, 0);  // bx0 = 1, by0 = 0, bx1 = 0, by1 = 0
             reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot)[3] = q;
         }
@@ -463,12 +474,13 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
             const TriUV uv = {poly[0].u, poly[0].v, poly[i + 1].u, poly[i + 1].v, poly[i + 2].u, poly[i + 2].v};
             const TileSpan sp = tile_span(e.rec);
             const bool big = sp.count() > kMaxBinsPerTri;
-            e.rec.binPos = big ? 0u : atomicAdd(&cntA[sp.ty0 * a.ntx + sp.tx0], 1u);
+            e.rec.order = slot;
             store_record(a, frame, e.rec, uv, slot);
-            if (big || sp.count() > 1) count_other_tiles(a, frame, sp, slot);
+            if (!big) append_desc(a, frame, sp.ty0 * a.ntx + sp.tx0, slot & ~31u, 1u << (slot & 31u));
+            if (big || sp.count() > 1) bin_other_tiles(a, frame, sp, slot);
             slot++;
         }
-        if (lane == 0) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = emitted;
+        if (lane == 0 && a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = emitted;
     }
 
     // TPF (renderer.go:436-441) and diagnostics: one atomic per warp

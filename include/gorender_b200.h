@@ -110,14 +110,14 @@ typedef struct grb_triangle_rec {
     float i0, i1, i2;                 /* vertex intensities                */
     int16_t bx0, by0, bx1, by1;       /* inclusive raster bbox after the tile-list rule */
     int32_t tex;                      /* texture id, -1 = face colour      */
-    uint32_t bin_pos;                 /* position in its first device tile's list */
+    uint32_t order;                   /* record slot == submission-order key      */
 } grb_triangle_rec;
 
 /* Per-frame statistics. */
 typedef struct grb_frame_stats {
     int64_t tpf;             /* Renderer.TPF (renderer.go:436-441)                  */
     int32_t triangles;       /* emitted triangles that reached the rasteriser       */
-    int32_t big_triangles;   /* of those, handled by the whole-tile cooperative path */
+    int32_t big_triangles;   /* of those, spanning more than 16 device tiles (frame-wide list) */
     int32_t out_of_domain;   /* triangles dropped: snapped |coord| > 16383 or NaN   */
     int32_t reserved;
 } grb_frame_stats;
@@ -141,7 +141,7 @@ int32_t grb_context_set_kernel_timing(grb_context *ctx, int32_t enable);
  * (Object.TransformedVertices, mesh.go:76) for grb_debug_read_transformed.  Off by default: the
  * frame path fuses the transform into the setup kernel and never materialises that array. */
 int32_t grb_context_set_stage_capture(grb_context *ctx, int32_t enable);
-/* out_ms[0..4] = transform, setup, bin-scan, bin-fill, raster; out_launches =
+/* out_ms[0..4] = transform (stage capture only), setup (incl. binning), 0, 0, raster; out_launches =
  * number of kernel launches accumulated.  Resets the accumulators. */
 int32_t grb_kernel_times(grb_context *ctx, double out_ms[5], int64_t *out_launches);
 /* Total kernel launches issued by this context since creation. */

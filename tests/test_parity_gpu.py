@@ -91,6 +91,7 @@ def test_stage_parity(name, device, oracle):
     try:
         fb, r = render(sc, device)
         tv = r.debug_transformed(0)
+        recs, uvs = r.debug_triangles(0)
     finally:
         device.set_stage_capture(False)
     ref = oracle.draw(r, sc.objects, sc.camera, record=True)
@@ -108,7 +109,6 @@ def test_stage_parity(name, device, oracle):
             assert np.array_equal(tv[base:base + n].view(np.uint32), want.view(np.uint32))
         base += n
 
-    recs, uvs = r.debug_triangles(0)
     tris = ref["triangles"]
     # the device keeps only triangles with a non-empty raster bbox that sit in some
     # reference tile list; filter the oracle's list the same way
