@@ -123,6 +123,26 @@ def tiny_far(w=320, h=240, **opt):
     return SceneDef(w, h, [_obj(geometry.geodesic_sphere(24), t=(0, 0, -20))], geometry.default_camera(), opt)
 
 
+def tiny_far_dense(w=320, h=240, **opt):
+    """72 000-triangle sphere squeezed into a handful of device tiles: a tile's list grows past its
+    in-place descriptor capacity, so the overflow list is exercised."""
+    return SceneDef(w, h, [_obj(geometry.geodesic_sphere(60), t=(0, 0, -12))], geometry.default_camera(), opt)
+
+
+def stacked_quads(w=96, h=96, layers=700, **opt):
+    """`layers` screen-filling quads at different depths plus coincident duplicates (depth ties): more
+    large triangles per tile than the block-wide queue holds, so the warp-sweep fallback runs too."""
+    verts, faces = [], []
+    for k in range(layers):
+        z = -1.0 - 0.01 * (k % 350)          # the second half repeats the depths of the first: exact ties
+        s = 4.0 + 0.001 * k
+        b = len(verts)
+        verts += [(-s, -s, z, 1), (s, -s, z, 1), (s, s, z, 1), (-s, s, z, 1)]
+        faces += [(b, b + 1, b + 2), (b, b + 2, b + 3)]
+    mesh = g.NewMesh(np.array(verts, np.float32), None, g.FaceArray(np.array(faces, np.int32)))
+    return SceneDef(w, h, [_obj(mesh)], g.Camera(Position=(0.3, 0.2, 3.0)), opt)
+
+
 def odd_size(w=333, h=211, **opt):
     """Width not a multiple of 4 and neither a multiple of the tile: scalar write-back path,
     ragged reference tiles."""
@@ -159,6 +179,8 @@ PINNED: Dict[str, Callable[[], SceneDef]] = {
     "inside_sphere": inside_sphere,
     "multi_object": multi_object,
     "tiny_far": tiny_far,
+    "tiny_far_dense": tiny_far_dense,
+    "stacked_quads": stacked_quads,
     "odd_size": odd_size,
     "empty": empty_scene,
     "big_triangles": big_triangles,
