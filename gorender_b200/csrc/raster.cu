@@ -126,7 +126,7 @@ struct WarpTris {            // one per warp, 32 triangles
     int a20[32], b20[32], c20[32];
     float w0[32], w1[32], w2[32];
     uint32_t slot[32];
-    uint32_t box[32];        // local x0 | local y0 << 5 | (bw-1) << 10
+    uint32_t box[32];        // local x0 | local y0 << 5 | (bw-1) << 10 | ceil(65536 / bw) << 15
 };
 constexpr int kFragRing = 64;
 constexpr int kLargeQueue = 1024;  // large triangles a block queues per round before falling back to warp sweeps
@@ -209,7 +209,9 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
                 wt.a20[lane] = e.a20; wt.b20[lane] = e.b20; wt.c20[lane] = e.c20;
                 wt.w0[lane] = r.w0; wt.w1[lane] = r.w1; wt.w2[lane] = r.w2;
                 wt.slot[lane] = slot;
-                wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)(bw - 1) << 10);
+                // ceil(65536 / bw): (j * inv) >> 16 == j / bw exactly for j < 32, bw <= 32
+                const uint32_t inv = (65536u + (uint32_t)bw - 1u) / (uint32_t)bw;
+                wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)(bw - 1) << 10) | (inv << 15);
                 area = n;
             } else {
                 large = true;
@@ -238,8 +240,7 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
         const int j = item - __shfl_sync(0xffffffffu, excl, t);
         const uint32_t box = wt.box[t];
         const int bw = (int)((box >> 10) & 31u) + 1;
-        // j / bw for j < 32: (j + 0.5) / bw is never within 1/64 of an integer
-        const int row = (int)(((float)j + 0.5f) * __frcp_rn((float)bw));
+        const int row = (int)(((uint32_t)j * (box >> 15)) >> 16);  // j / bw
         const int lx = (int)(box & 31u) + (j - row * bw), ly = (int)((box >> 5) & 31u) + row;
         const int x = tileX + lx, y = tileY + ly;
         const int f01 = wt.a01[t] * x + wt.b01[t] * y + wt.c01[t];
