@@ -31,7 +31,8 @@ namespace gr {
 
 constexpr int kRasterThreads = 256;
 constexpr int kRasterBlocksPerSM = 6;  // resident blocks per SM the register budget is held to
-constexpr int kSmallArea = 32;  // bbox∩tile pixels up to which one thread rasterises a triangle alone
+constexpr int kSmallArea = 32;  // bbox∩tile pixels up to which a triangle takes the warp-level coarse/fine path
+constexpr int kSmallWidth = 8;  // ... and the widest bbox row that path walks
 constexpr unsigned long long kBackgroundKey = 0x407FFFFFull << 32;  // orderable(-1.0f) (rasterizer.go:37)
 
 __device__ __forceinline__ uint32_t orderable(float z) {
@@ -112,9 +113,10 @@ __device__ __forceinline__ uchar4 sample_texture(const TexDev &t, float u, float
 //
 // A warp takes 32 list entries at a time.  Each lane sets up its triangle (edge functions, the
 // bbox clipped to the tile) into a per-warp shared-memory table, struct-of-arrays so that lanes
-// reading different triangles hit different banks.  The bbox pixels of all 32 triangles are then
-// flattened into one work list (warp prefix sum of the areas) and tested 32 at a time — coarse
-// stage, integer edge functions only.  Covered (triangle, pixel) pairs are pushed into a
+// reading different triangles hit different banks.  The bbox ROWS of all 32 triangles are then
+// flattened into one work list (warp prefix sum of the row counts); a lane takes a row, evaluates
+// the three edge functions once at its left end and steps along its few pixels — coarse stage,
+// integer adds only.  Covered (triangle, pixel) pairs are pushed into a
 // per-warp ring; whenever 32 are available the fine stage runs with every lane busy: 5 IEEE
 // divides for zRec (rasterizer.go:149-153) and a shared-memory atomic max on the pixel's key.
 // One lane per triangle would execute the divide sequence at the occupancy of the rare covered
@@ -126,7 +128,7 @@ struct WarpTris {            // one per warp, 32 triangles
     int a20[32], b20[32], c20[32];
     float w0[32], w1[32], w2[32];
     uint32_t slot[32];
-    uint32_t box[32];        // local x0 | local y0 << 5 | (bw-1) << 10 | ceil(65536 / bw) << 15
+    uint32_t box[32];        // local x0 | local y0 << 5 | bw << 10
 };
 constexpr int kFragRing = 64;
 constexpr int kLargeQueue = 1024;  // large triangles a block queues per round before falling back to warp sweeps
@@ -194,43 +196,43 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
                                               int tileX1, int tileY1, unsigned long long *keys, uint32_t *largeQ,
                                               int *largeCount) {
     const unsigned ltMask = (1u << lane) - 1u;
-    int area = 0;
+    int rows = 0;   // bbox rows of this lane's triangle inside the tile (0: nothing for the small path)
     bool large = false;
     if (have) {
         const TriRec r = load_rec(rec + slot);
         const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
         const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
         if (x0 <= x1 && y0 <= y1) {
-            const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
-            if (n <= kSmallArea) {
+            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+            if (bw <= kSmallWidth && bw * bh <= kSmallArea) {
                 const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
                 wt.a01[lane] = e.a01; wt.b01[lane] = e.b01; wt.c01[lane] = e.c01;
                 wt.a12[lane] = e.a12; wt.b12[lane] = e.b12; wt.c12[lane] = e.c12;
                 wt.a20[lane] = e.a20; wt.b20[lane] = e.b20; wt.c20[lane] = e.c20;
                 wt.w0[lane] = r.w0; wt.w1[lane] = r.w1; wt.w2[lane] = r.w2;
                 wt.slot[lane] = slot;
-                // ceil(65536 / bw): (j * inv) >> 16 == j / bw exactly for j < 32, bw <= 32
-                const uint32_t inv = (65536u + (uint32_t)bw - 1u) / (uint32_t)bw;
-                wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)(bw - 1) << 10) | (inv << 15);
-                area = n;
+                wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)bw << 10);
+                rows = bh;
             } else {
                 large = true;
             }
         }
     }
-    // ---- small triangles: flatten the 32 bboxes into one pixel list
-    int incl = area;
+    // ---- small triangles: flatten the bbox ROWS of the 32 triangles into one list; a lane takes a
+    //      row, sets the three edge functions up once and walks its (at most kSmallWidth) pixels
+    int incl = rows;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += v;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int excl = incl - area;
+    const int excl = incl - rows;
     __syncwarp();
     for (int item0 = 0; item0 < total; item0 += 32) {
+        const bool active = item0 + lane < total;
         const int item = min(item0 + lane, total - 1);
-        // triangle owning this pixel: number of lanes whose inclusive sum is <= item
+        // triangle owning this row: number of lanes whose inclusive sum is <= item
         int t = 0;
 #pragma unroll
         for (int step = 16; step >= 1; step >>= 1) {
@@ -239,21 +241,28 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
         }
         const int j = item - __shfl_sync(0xffffffffu, excl, t);
         const uint32_t box = wt.box[t];
-        const int bw = (int)((box >> 10) & 31u) + 1;
-        const int row = (int)(((uint32_t)j * (box >> 15)) >> 16);  // j / bw
-        const int lx = (int)(box & 31u) + (j - row * bw), ly = (int)((box >> 5) & 31u) + row;
-        const int x = tileX + lx, y = tileY + ly;
-        const int f01 = wt.a01[t] * x + wt.b01[t] * y + wt.c01[t];
-        const int f12 = wt.a12[t] * x + wt.b12[t] * y + wt.c12[t];
-        const int f20 = wt.a20[t] * x + wt.b20[t] * y + wt.c20[t];
-        const bool inside = (item0 + lane < total) && ((f01 & f12 & f20) < 0);
-        const unsigned m = __ballot_sync(0xffffffffu, inside);
-        if (inside) ring[(qTail + __popc(m & ltMask)) & (kFragRing - 1)] = ((uint32_t)t << 10) | ((uint32_t)ly << 5) | (uint32_t)lx;
-        qTail += __popc(m);
-        __syncwarp();
-        if (qTail - qHead >= 32) {
-            fine_stage(wt, ring, qHead, 32, lane, tileX, tileY, keys);
-            qHead += 32;
+        const int bw = active ? (int)(box >> 10) : 0;
+        const int lx0 = (int)(box & 31u), ly = (int)((box >> 5) & 31u) + j;
+        const int x = tileX + lx0, y = tileY + ly;
+        const int a01 = wt.a01[t], a12 = wt.a12[t], a20 = wt.a20[t];
+        int f01 = a01 * x + wt.b01[t] * y + wt.c01[t];
+        int f12 = a12 * x + wt.b12[t] * y + wt.c12[t];
+        int f20 = a20 * x + wt.b20[t] * y + wt.c20[t];
+        const uint32_t tag = ((uint32_t)t << 10) | ((uint32_t)ly << 5);
+        const int maxBw = __reduce_max_sync(0xffffffffu, bw);
+        for (int k = 0; k < maxBw; k++) {
+            const bool inside = k < bw && (f01 & f12 & f20) < 0;
+            const unsigned m = __ballot_sync(0xffffffffu, inside);
+            if (m) {
+                if (inside) ring[(qTail + __popc(m & ltMask)) & (kFragRing - 1)] = tag | (uint32_t)(lx0 + k);
+                qTail += __popc(m);
+                __syncwarp();
+                if (qTail - qHead >= 32) {
+                    fine_stage(wt, ring, qHead, 32, lane, tileX, tileY, keys);
+                    qHead += 32;
+                }
+            }
+            f01 += a01; f12 += a12; f20 += a20;
         }
     }
     // the table is rewritten by the next batch: drain what is left
