@@ -400,6 +400,8 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.tileRowBegin = rowBegin;
     a.tileRowEnd = rowEnd;
     std::memcpy(a.screen.m, prm->screen, 64);
+    a.fma.negZero = make_float2(-0.0f, -0.0f);
+    a.fma.one = make_float2(1.0f, 1.0f);
     a.lx = prm->light[0]; a.ly = prm->light[1]; a.lz = prm->light[2];
     a.options = prm->options;
     a.zNear = prm->z_near;

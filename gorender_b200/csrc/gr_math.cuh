@@ -77,6 +77,43 @@ GR_HD float4 mat_vec(const float *m, float4 v) {
     return make_float4(mat_row(m, v), mat_row(m + 4, v), mat_row(m + 8, v), mat_row(m + 12, v));
 }
 
+#ifdef __CUDACC__
+// Packed matrix * vector on Blackwell's two-wide FP32 pipe.  There is no separately rounded packed
+// multiply or add in SASS (ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with explicit
+// .rn and -fmad=false), so each is spelled as an FMA whose result is exactly the rounded product
+// or sum:  a*b == fma(a, b, -0)  and  a+b == fma(a, 1, b)  (one rounding each, signs of zero
+// included).  The -0 and 1 operands must be RUN-TIME values (FmaConsts, filled by the host): with
+// literals the compiler simplifies the FMAs back to mul / add and ptxas then fuses those — a
+// one-ulp difference in clip-space w that the parity tests catch.  14 FFMA2 instead of 16 FMUL +
+// 12 FADD, bit-identical to mat_vec().
+struct FmaConsts {
+    float2 negZero, one;     // (-0, -0) and (1, 1)
+};
+struct Mat4P {
+    float2 c01[4], c23[4];   // column k of rows (0,1) and of rows (2,3)
+    FmaConsts k;
+};
+GR_D Mat4P pack_mat(const float *m, const FmaConsts &k) {
+    Mat4P p;
+    p.k = k;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        p.c01[k] = make_float2(m[k], m[4 + k]);
+        p.c23[k] = make_float2(m[8 + k], m[12 + k]);
+    }
+    return p;
+}
+GR_D float4 mat_vec(const Mat4P &p, float4 v) {
+    auto mul2 = [&](float2 a, float2 b) { return __ffma2_rn(a, b, p.k.negZero); };
+    auto add2 = [&](float2 a, float2 b) { return __ffma2_rn(a, p.k.one, b); };
+    const float2 x = make_float2(v.x, v.x), y = make_float2(v.y, v.y), z = make_float2(v.z, v.z), w = make_float2(v.w, v.w);
+    // row r: ((m[r][0]*x + m[r][1]*y) + m[r][2]*z) + m[r][3]*w  (asm_amd64.s:33-40)
+    const float2 r01 = add2(add2(add2(mul2(p.c01[0], x), mul2(p.c01[1], y)), mul2(p.c01[2], z)), mul2(p.c01[3], w));
+    const float2 r23 = add2(add2(add2(mul2(p.c23[0], x), mul2(p.c23[1], y)), mul2(p.c23[2], z)), mul2(p.c23[3], w));
+    return make_float4(r01.x, r01.y, r23.x, r23.y);
+}
+#endif
+
 // Go builtin min/max on floats propagate NaN (renderer.go:229-232).
 GR_HD float gomin(float a, float b) {
     if (a != a || b != b) return a + b;  // NaN

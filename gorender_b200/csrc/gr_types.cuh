@@ -145,6 +145,7 @@ struct DrawArgs {
     int32_t tileRowBegin, tileRowEnd;  // strip, in tile rows
     // params
     Mat4 screen;
+    FmaConsts fma;              // run-time -0 / 1 for the packed FFMA2 products (gr_math.cuh)
     float lx, ly, lz;
     uint32_t options;
     float zNear, zFar;

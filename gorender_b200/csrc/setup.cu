@@ -280,7 +280,7 @@ __device__ __forceinline__ void bin_other_tiles(const DrawArgs &a, int frame, co
 
 // renderer.go:328-337: xyz(normalize4(world * n)) . L, with w (=1, translated)
 // taking part in the length
-__device__ __forceinline__ float light_intensity(const float *world, float4 n, float lx, float ly, float lz) {
+__device__ __forceinline__ float light_intensity(const Mat4P &world, float4 n, float lx, float ly, float lz) {
     const float4 wn = mat_vec(world, n);
     const float len = fsqrt(fadd(fadd(fadd(fmul(wn.x, wn.x), fmul(wn.y, wn.y)), fmul(wn.z, wn.z)), fmul(wn.w, wn.w)));
     const float nx = fdiv(wn.x, len), ny = fdiv(wn.y, len), nz = fdiv(wn.z, len);
@@ -295,7 +295,7 @@ struct __align__(16) StagedFace {
 };
 
 template <bool CLIP>
-__global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant__ DrawArgs a) {
+__global__ void __launch_bounds__(kFaceBlock, 5) setup_kernel(const __grid_constant__ DrawArgs a) {
     const int frame = blockIdx.y;
     const int fb = blockIdx.x;
     const int o = a.fblkObj[fb];
@@ -319,9 +319,10 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
     bool alive = f < m.nf;
     float4 v0, v1, v2;
     if (alive) {
-        v0 = mat_vec(fo.mvp, __ldg(&m.cv[0][f]));
-        v1 = mat_vec(fo.mvp, __ldg(&m.cv[1][f]));
-        v2 = mat_vec(fo.mvp, __ldg(&m.cv[2][f]));
+        const Mat4P mvp = pack_mat(fo.mvp, a.fma);
+        v0 = mat_vec(mvp, __ldg(&m.cv[0][f]));
+        v1 = mat_vec(mvp, __ldg(&m.cv[1][f]));
+        v2 = mat_vec(mvp, __ldg(&m.cv[2][f]));
         if (a.options & GRB_OPT_BACKFACE_CULLING) {
             // facingCamera (renderer.go:246-250) on clip-space xyz
             const float e1x = fsub(v1.x, v0.x), e1y = fsub(v1.y, v0.y), e1z = fsub(v1.z, v0.z);
@@ -359,20 +360,28 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
             if (w < (int)warpInBlock) base += c;
             nAlive += c;
         }
-        if (alive) {
-            const uint32_t rank = __popc(aliveMask & ltMask);
-            staged[base + rank] = {v0, v1, v2};
-            stagedMeta[base + rank][0] = (uint32_t)f;
-            stagedMeta[base + rank][1] = slot0 + rank;
-        }
-        __syncthreads();
-        alive = threadIdx.x < nAlive;
-        if (warpInBlock * 32 >= nAlive) return;  // whole warp idle
-        if (alive) {
-            const StagedFace sf = staged[threadIdx.x];
-            v0 = sf.v0; v1 = sf.v1; v2 = sf.v2;
-            f = (int)stagedMeta[threadIdx.x][0];
-            slot = stagedMeta[threadIdx.x][1];
+        if (nAlive == 0) return;
+        slot = slot0 + __popc(aliveMask & ltMask);
+        // Compaction pays only when it frees whole warps (block-uniform decision): a block whose
+        // survivors still need all 8 warps keeps every face where it is.
+        if (nAlive <= kFaceBlock - 32) {
+            if (alive) {
+                const uint32_t rank = __popc(aliveMask & ltMask);
+                staged[base + rank] = {v0, v1, v2};
+                stagedMeta[base + rank][0] = (uint32_t)f;
+                stagedMeta[base + rank][1] = slot;
+            }
+            __syncthreads();
+            alive = threadIdx.x < nAlive;
+            if (warpInBlock * 32 >= nAlive) return;  // whole warp idle
+            if (alive) {
+                const StagedFace sf = staged[threadIdx.x];
+                v0 = sf.v0; v1 = sf.v1; v2 = sf.v2;
+                f = (int)stagedMeta[threadIdx.x][0];
+                slot = stagedMeta[threadIdx.x][1];
+            }
+        } else if (aliveMask == 0) {
+            return;  // whole warp culled
         }
     }
 
@@ -381,12 +390,13 @@ __global__ void __launch_bounds__(kFaceBlock) setup_kernel(const __grid_constant
     int tex = -1;
     if (alive) {
         if (a.options & GRB_OPT_LIGHTING) {
+            const Mat4P world = pack_mat(fo.world, a.fma);
             if (m.nvn != 0 && !(a.options & GRB_OPT_FLAT_SHADING)) {
-                in0 = light_intensity(fo.world, __ldg(&m.cn[0][f]), a.lx, a.ly, a.lz);
-                in1 = light_intensity(fo.world, __ldg(&m.cn[1][f]), a.lx, a.ly, a.lz);
-                in2 = light_intensity(fo.world, __ldg(&m.cn[2][f]), a.lx, a.ly, a.lz);
+                in0 = light_intensity(world, __ldg(&m.cn[0][f]), a.lx, a.ly, a.lz);
+                in1 = light_intensity(world, __ldg(&m.cn[1][f]), a.lx, a.ly, a.lz);
+                in2 = light_intensity(world, __ldg(&m.cn[2][f]), a.lx, a.ly, a.lz);
             } else {
-                in0 = in1 = in2 = light_intensity(fo.world, __ldg(&m.fnormals[f]), a.lx, a.ly, a.lz);
+                in0 = in1 = in2 = light_intensity(world, __ldg(&m.fnormals[f]), a.lx, a.ly, a.lz);
             }
         }
         // drawProjection (renderer.go:176-178): ShowTextures off => nil texture
