@@ -310,9 +310,6 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
     }
 }
 
-// n-th (0-based) set bit of mask
-__device__ __forceinline__ int nth_set_bit(uint32_t mask, int n) { return __fns(mask, 0, n + 1); }
-
 // Block-wide pass over the queued large triangles: every thread owns 4 consecutive pixels of the
 // tile and keeps their keys in registers while it walks the queue; no atomics.
 __device__ __forceinline__ void coop_pass(const uint32_t *largeQ, int nq, const TriRec *rec, int gx, int gy, int px, int py,
