@@ -109,6 +109,7 @@ SIGNATURES = {
     "grb_frame_stats_read": (C.c_int32, [_VP, C.c_int32, _VP]),
     "grb_read_frames": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     "grb_read_frames_async": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
+    "grb_framebuffer_wait": (C.c_int32, [_VP]),
     "grb_matrix_multiply_vec4_batch": (C.c_int32, [_VP, c_float_p, _VP, C.c_int64]),
     "grb_matrix_multiply_vec4_batch_device": (C.c_int32, [_VP, c_float_p, _VP, C.c_int64]),
     "grb_debug_read_transformed": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int64, C.POINTER(C.c_int64)]),

@@ -804,6 +804,17 @@ int32_t grb_read_frames(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, i
     return GRB_OK;
 }
 
+int32_t grb_framebuffer_wait(grb_framebuffer *fb) {
+    if (!fb) return GRB_ERR_INVALID;
+    grb_context *ctx = fb->ctx;
+    if (int32_t r = set_device(ctx)) return r;
+    if (fb->pendingRead) {
+        CK(ctx, cudaEventSynchronize(fb->readDone));
+        fb->pendingRead = false;
+    }
+    return GRB_OK;
+}
+
 int32_t grb_matrix_multiply_vec4_batch_device(grb_context *ctx, const float m[16], void *device_vecs, int64_t n) {
     if (!ctx || !m || (n > 0 && !device_vecs) || n < 0) return fail(ctx, GRB_ERR_INVALID, "bad argument");
     if (int32_t r = set_device(ctx)) return r;

@@ -7,6 +7,7 @@
 //   -start K         spin frames to skip before the first rendered one
 //   -ppm FILE        write the last frame as a binary PPM
 //   -raw FILE        write the last frame's RGBA8 pixels followed by the f32 z-buffer
+//   -async           streaming loop: DrawAsync + SwapBuffers, the read-back of frame i overlaps frame i+1
 //   -matrices        print world / mvp of the last frame as hex words (host-math cross-check, no GPU needed)
 //   -texdump         print size, type and an FNV-1a hash of the premultiplied texels of a PNG (no GPU needed)
 #include <chrono>
@@ -30,7 +31,7 @@ static void printMatrix(const char *name, const Matrix &m) {
 
 int main(int argc, char **argv) {
     int width = 1280, height = 720, frames = 100, start = 0;
-    bool matricesOnly = false, texDump = false;
+    bool matricesOnly = false, texDump = false, async = false;
     std::string ppm, raw, file;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -43,6 +44,7 @@ int main(int argc, char **argv) {
         else if (a == "-raw") raw = next();
         else if (a == "-matrices") matricesOnly = true;
         else if (a == "-texdump") texDump = true;
+        else if (a == "-async") async = true;
         else file = a;
     }
     if (file.empty()) {
@@ -85,11 +87,25 @@ int main(int argc, char **argv) {
         FrameBuffer fb(dev, width, height);
         Renderer renderer(fb);
         const auto t0 = std::chrono::steady_clock::now();
-        for (int f = 0; f < frames; f++) {
-            renderer.Draw(scene.Objects, camera);
-            if (f + 1 < frames) {
-                fb.SwapBuffers();
-                for (auto &o : scene.Objects) o->Rotation.Y += 0.01f;
+        if (async) {
+            // main.go:198-227 with the present step replaced by "the frame is in Pixels2"
+            for (int f = 0; f < frames; f++) {
+                renderer.DrawAsync(scene.Objects, camera);   // frame f -> Pixels (kernels, then PCIe)
+                if (f > 0) fb.WaitFront();                   // frame f-1 has landed in Pixels2: present it here
+                fb.SwapBuffers();                            // frame f is now heading for Pixels2
+                if (f + 1 < frames)
+                    for (auto &o : scene.Objects) o->Rotation.Y += 0.01f;
+            }
+            fb.WaitFront();
+            fb.SwapBuffers();                                // leave the last frame in Pixels, like Draw does
+            renderer.Draw(scene.Objects, camera);            // one synchronous draw for TPF / depth of the last frame
+        } else {
+            for (int f = 0; f < frames; f++) {
+                renderer.Draw(scene.Objects, camera);
+                if (f + 1 < frames) {
+                    fb.SwapBuffers();
+                    for (auto &o : scene.Objects) o->Rotation.Y += 0.01f;
+                }
             }
         }
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -582,20 +582,56 @@ private:
     std::vector<MeshPtr> keepM_;
 };
 
+// Pinned (page-locked) host array: the read-back of a frame runs at PCIe speed only into pinned
+// memory, so FrameBuffer keeps Pixels / Pixels2 / ZBuffer there (grb_host_alloc).
+template <typename T> class PinnedArray {
+public:
+    explicit PinnedArray(size_t n) : n_(n), p_(static_cast<T *>(grb_host_alloc(n * sizeof(T)))) {
+        if (!p_) throw std::bad_alloc();
+        std::memset(p_, 0, n * sizeof(T));
+    }
+    ~PinnedArray() { grb_host_free(p_); }
+    PinnedArray(const PinnedArray &) = delete;
+    PinnedArray &operator=(const PinnedArray &) = delete;
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    size_t size() const { return n_; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    void swap(PinnedArray &o) { std::swap(p_, o.p_); std::swap(n_, o.n_); }
+
+private:
+    size_t n_;
+    T *p_;
+};
+
 struct FrameBuffer {  // rasterizer.go:7-23
     int Width, Height;
-    std::vector<float> ZBuffer;
-    std::vector<uint8_t> Pixels, Pixels2;  // RGBA8
+    PinnedArray<float> ZBuffer;
+    PinnedArray<uint8_t> Pixels, Pixels2;  // RGBA8; Pixels is what Draw fills, Pixels2 what is presented
     Device *dev;
-    grb_framebuffer *handle = nullptr;
+    // Two device framebuffers: `handle` belongs to Pixels, `handle2` to Pixels2, and they swap
+    // together, so a frame still crossing PCIe into Pixels2 never blocks the draw into Pixels
+    // (the reference overlaps render and present the same way, main.go:198-227).
+    grb_framebuffer *handle = nullptr, *handle2 = nullptr;
     FrameBuffer(Device &d, int width, int height)
         : Width(width), Height(height), ZBuffer((size_t)width * height), Pixels((size_t)width * height * 4),
           Pixels2((size_t)width * height * 4), dev(&d) {
         d.check(grb_framebuffer_create(d.ctx(), width, height, 1, &handle), "grb_framebuffer_create");
+        d.check(grb_framebuffer_create(d.ctx(), width, height, 1, &handle2), "grb_framebuffer_create");
     }
-    ~FrameBuffer() { grb_framebuffer_destroy(handle); }
+    ~FrameBuffer() {
+        grb_framebuffer_destroy(handle);
+        grb_framebuffer_destroy(handle2);
+    }
     FrameBuffer(const FrameBuffer &) = delete;
-    void SwapBuffers() { Pixels.swap(Pixels2); }  // rasterizer.go:32-34
+    // rasterizer.go:32-34.  Does not wait: after DrawAsync + SwapBuffers the frame is on its way
+    // into Pixels2; WaitFront() blocks until it has landed.
+    void SwapBuffers() {
+        Pixels.swap(Pixels2);
+        std::swap(handle, handle2);
+    }
+    void WaitFront() { dev->check(grb_framebuffer_wait(handle2), "grb_framebuffer_wait"); }
 };
 
 class Renderer {  // renderer.go:83-164
@@ -633,8 +669,30 @@ public:
         mvp = Multiply(mvp, world);
     }
 
+    // Streaming form: queue the draw and the read-back of pixels into fb.Pixels and return.  The
+    // frame is complete after fb.SwapBuffers(); fb.WaitFront().  Depth stays on the device and TPF
+    // is not updated (use Draw for those).
+    void DrawAsync(const std::vector<ObjectPtr> &objects, const Camera &camera) {
+        Device &dev = *fb_.dev;
+        grb_draw_params p{};
+        pack(objects, camera, p);
+        dev.check(grb_draw_async(dev.ctx(), fb_.handle, 0, 1, objs_.empty() ? nullptr : objs_.data(), (int32_t)objs_.size(), &p), "grb_draw_async");
+        dev.check(grb_read_frames_async(dev.ctx(), fb_.handle, 0, 1, fb_.Pixels.data(), nullptr), "grb_read_frames_async");
+    }
+
     // renderer.go:443-483: side effects on fb.Pixels, fb.ZBuffer, TPF; throws where Go would panic
     void Draw(const std::vector<ObjectPtr> &objects, const Camera &camera) {
+        Device &dev = *fb_.dev;
+        grb_draw_params p{};
+        pack(objects, camera, p);
+        grb_frame_stats st{};
+        dev.check(grb_draw(dev.ctx(), fb_.handle, 0, 1, objs_.empty() ? nullptr : objs_.data(), (int32_t)objs_.size(), &p, &st), "grb_draw");
+        TPF = (int)st.tpf;
+        dev.check(grb_read_frames(dev.ctx(), fb_.handle, 0, 1, fb_.Pixels.data(), fb_.ZBuffer.data()), "grb_read_frames");
+    }
+
+private:
+    void pack(const std::vector<ObjectPtr> &objects, const Camera &camera, grb_draw_params &p) {
         Device &dev = *fb_.dev;
         objs_.resize(objects.size());
         for (size_t i = 0; i < objects.size(); i++) {
@@ -644,7 +702,6 @@ public:
             std::memcpy(objs_[i].world, world.data(), 64);
             std::memcpy(objs_[i].mvp, mvp.data(), 64);
         }
-        grb_draw_params p{};
         Matrix screen = NewScreenMatrix(fb_.Width, fb_.Height);     // renderer.go:264
         std::memcpy(p.screen, screen.data(), 64);
         Vec3 light = Normalize(Vec3{-1, 1, 1});                     // renderer.go:265
@@ -652,13 +709,8 @@ public:
         p.options = options();
         p.z_near = zNear_; p.z_far = zFar_;
         p.ref_tiles = numTiles_;
-        grb_frame_stats st{};
-        dev.check(grb_draw(dev.ctx(), fb_.handle, 0, 1, objs_.empty() ? nullptr : objs_.data(), (int32_t)objs_.size(), &p, &st), "grb_draw");
-        TPF = (int)st.tpf;
-        dev.check(grb_read_frames(dev.ctx(), fb_.handle, 0, 1, fb_.Pixels.data(), fb_.ZBuffer.data()), "grb_read_frames");
     }
 
-private:
     FrameBuffer &fb_;
     float aspectX_, fovY_, zNear_, zFar_;
     int numTiles_;

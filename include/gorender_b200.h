@@ -202,6 +202,12 @@ int32_t grb_read_frames(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, i
 int32_t grb_read_frames_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
                               uint8_t *pixels, float *zbuffer);
 
+/* Blocks until the most recent grb_read_frames_async of `fb` has landed in host memory (returns
+ * at once if there is none).  Together with grb_draw_async this is the streaming form of the
+ * reference's render / present double buffer (main.go:198-227, rasterizer.go:32-34): draw frame
+ * i+1 into a second framebuffer while frame i is still crossing PCIe. */
+int32_t grb_framebuffer_wait(grb_framebuffer *fb);
+
 /* ---- the build-tag seam: matrixMultiplyVec4Batch (asm_amd64.go:8-11,
  *      asm_amd64.s:7-50, asm_purego.go:9-19).  In place on n host Vec4s. */
 int32_t grb_matrix_multiply_vec4_batch(grb_context *ctx, const float m[16], float *vecs, int64_t n);

@@ -125,3 +125,7 @@ def test_headless_driver_matches_python_path(tmp_path, device):
     assert f"tpf={r.TPF} " in out
     assert np.array_equal(px, fb.Pixels) and np.array_equal(z.view(np.uint32), fb.ZBuffer.view(np.uint32))
     assert (fb.ZBuffer > -1).sum() > 10000
+    # the streaming loop (DrawAsync / SwapBuffers / WaitFront) ends on the same frame
+    raw2 = tmp_path / "out_async.bin"
+    run("-w", 640, "-h", 360, "-frames", 3, "-async", "-raw", raw2, obj)
+    assert np.array_equal(np.fromfile(raw2, dtype=np.uint8), blob)
