@@ -163,10 +163,19 @@ __device__ __forceinline__ TriRec load_rec(const TriRec *p) {
     return r;
 }
 
-// Clear (rasterizer.go:36-44) + DotGrid step 10 (:46-52) for one pixel.
-__device__ __forceinline__ uchar4 background(int x, int y) {
-    const bool dot = (x >= 10) && (y >= 10) && (x % 10 == 0) && (y % 10 == 0);
-    return dot ? make_uchar4(100, 100, 100, 255) : make_uchar4(50, 50, 50, 255);
+// Clear (rasterizer.go:36-44) + DotGrid step 10 (:46-52) for the four pixels (gx..gx+3, gy) of a
+// thread: bit k of the result is set where pixel gx+k is a grid dot.  One modulo per axis.
+__device__ __forceinline__ unsigned dot_mask(int gx, int gy) {
+    if (gy < 10 || gy % 10 != 0) return 0u;
+    const int r = gx % 10;  // gx + k is a multiple of 10 iff r + k is 0 or 10
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if ((r + k == 0 || r + k == 10) && gx + k >= 10) m |= 1u << k;
+    return m;
+}
+__device__ __forceinline__ uchar4 background(unsigned dots, int k) {
+    return (dots >> k) & 1u ? make_uchar4(100, 100, 100, 255) : make_uchar4(50, 50, 50, 255);
 }
 
 // Four consecutive pixels of one row: one 128-bit store each for colour and depth.
@@ -401,9 +410,10 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
         if (inImage) {
             uchar4 col[4];
             float zo[4];
+            const unsigned dots = dot_mask(gx, gy);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                col[k] = background(gx + k, gy);
+                col[k] = background(dots, k);
                 zo[k] = -1.0f;
             }
             write_quad(a, frame, gx, gy, col, zo);
@@ -522,13 +532,14 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     TriRec r;
     Edges e;
     uint32_t have = 0;  // slot + 1 of the record held in r / e
+    const unsigned dots = dot_mask(gx, gy);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int x = gx + k;
         const unsigned long long key = keys[py * kTile + px + k];
         const uint32_t slot1 = (uint32_t)key;
         if (slot1 == 0) {
-            col[k] = background(x, gy);
+            col[k] = background(dots, k);
             zo[k] = -1.0f;
             continue;
         }
