@@ -285,6 +285,15 @@ class Renderer:
         return o
 
     def draw_params(self, rows: Optional[Tuple[int, int]] = None) -> _cabi.grb_draw_params:
+        key = (rows, self.options(), self.numTiles, float(self.zNear), float(self.zFar), self.fb.Width, self.fb.Height)
+        cached = getattr(self, "_params_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        p = self._build_draw_params(rows)
+        self._params_cache = (key, p)
+        return p
+
+    def _build_draw_params(self, rows: Optional[Tuple[int, int]] = None) -> _cabi.grb_draw_params:
         p = _cabi.grb_draw_params()
         screen = vm.NewScreenMatrix(self.fb.Width, self.fb.Height)          # renderer.go:264
         light = vm.light_direction()                                        # renderer.go:265
