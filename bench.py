@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+WORKLOAD = ("C3: 200k-triangle geodesic sphere (n=100), 1280x720, flat shading, untextured, default camera, "
+            "demo spin (BASELINE.json configs[2])")
 WIDTH, HEIGHT = 1280, 720
 SPHERE_N = 100            # 20*n^2 = 200 000 faces, 10*n^2+2 = 100 002 vertices
 METRIC = "Mtriangles/s (submitted scene triangles x FPS), 200k-tri mesh @1280x720"
@@ -50,7 +52,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per step")
     ap.add_argument("--batch", type=int, default=64, help="frames per batched Draw call")
-    ap.add_argument("--cpu-sample-frames", type=int, default=400, help="frames of the CPU baseline sample")
+    ap.add_argument("--cpu-sample-frames", type=int, default=2000, help="frames of the CPU baseline sample (~14 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="frames", choices=["frames", "strips"],
                     help="frames: frame-parallel C3 batches (the headline metric); strips: sort-first screen strips "
@@ -171,7 +173,7 @@ def run_reference(args, rank: int):
     objs, cam = build_scene()
     r = scene_defs.SceneDef(WIDTH, HEIGHT, objs, cam).renderer(None)
     threads = max(16, 1)  # numTiles workers (renderer.go:151-155)
-    frames = max(1, min(args.frames, 8))  # bounded sample per step
+    frames = max(1, min(args.frames, 64))  # bounded sample per step: 64 consecutive frames (~0.45 s of CPU)
     nfaces = sum(len(o.Mesh.Faces) for o in objs)
     nsteps = args.warmup + args.steps
     timer = orc.sequence_timer(r, objs, [cam] * (nsteps * frames), spin_frames(0, nsteps * frames), threads=threads)
@@ -190,8 +192,7 @@ def run_reference(args, rank: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "fps": fps, "mtps_hud": fps * tpf / 1e6,
-        "config": {"workload": "C3: 200k-triangle geodesic sphere (n=100), 1280x720, flat shading, untextured, "
-                               "default camera, demo spin", "frames_per_step": frames,
+        "config": {"workload": WORKLOAD, "frames_per_step": frames,
                    "note": "CPU restatement of the reference (C++, oracle/); Go is not installed in this image"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "threads": threads, "kind": "port",
                          "sample": sample},
@@ -473,8 +474,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "dtype": "f32", "data": "synthetic", "fps": fps,
             "mtps_hud": fps * float(stats["tpf"].mean()) / 1e6,
             "config": {
-                "workload": "C3: 200k-triangle geodesic sphere (n=100), 1280x720, flat shading, untextured, "
-                            "default camera, demo spin (BASELINE.json configs[2])",
+                "workload": WORKLOAD,
                 "frames_per_step": F, "frames_per_draw_call": B, "parallelism": f"frame-parallel x{world}",
                 "l2": f"no flush needed: every batched draw writes {B} x 7.4 MB of framebuffers and ~{B * 12} MB of "
                       "intermediates, far more than the 126 MB L2",
