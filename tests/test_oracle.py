@@ -180,3 +180,32 @@ def test_texture_sample_wrap(oracle):
     assert oracle.texture_sample(slow, 0.9, -0.4)[:2] == (0, 0)            # negative idx clamps to texel 0
     solid = g.NewColorTexture((1, 2, 3, 4))
     assert oracle.texture_sample(solid, 0.3, 0.3) == (1, 2, 3, 4)
+
+
+def test_oracle_against_reference_c_prototype(oracle):
+    """oracle/_ref/libref_cmatrix.so is the reference's own c/matrix_amd64.c (SSE prototype of
+    matrixMultiplyVec4Batch), compiled unmodified by oracle/build_ref.sh.  It sums
+    (p1+p2)+(p3+p4) while the Go assembly sums ((p1+p2)+p3)+p4, so: exact
+    agreement where the two orders coincide (z == 0), a few ulp elsewhere."""
+    import ctypes as C
+
+    path = os.path.join(os.path.dirname(workloads.GOLDEN_DIR), "..", "oracle", "_ref", "libref_cmatrix.so")
+    path = os.path.normpath(path)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (no reference checkout on this machine)")
+    ref = C.CDLL(path)
+    ref.matrix_multiply_vec4.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(5)
+    m = vm.Multiply(vm.NewTranslationMatrix(1, 2, 3), vm.Multiply(vm.NewRotationMatrix(0.1, 0.2, 0.3), vm.NewIdentityMatrix()))
+    cols = np.ascontiguousarray(m.T)                      # the prototype takes the matrix column-major
+    buf = (C.c_char * 80)()
+    base = (C.addressof(buf) + 15) & ~15                 # __m128 loads need 16-byte alignment
+    C.memmove(base, cols.ctypes.data, 64)
+    v = (rng.standard_normal((5000, 4)) * 10).astype(np.float32)
+    v[:2500, 2] = 0.0                                     # z == 0: both summation orders give the same bits
+    want = oracle.matvec4_batch(m, v)
+    got = np.ascontiguousarray(v.copy())
+    ref.matrix_multiply_vec4(C.c_void_p(base), C.c_void_p(got.ctypes.data), len(got))
+    assert np.array_equal(got[:2500].view(np.uint32), want[:2500].view(np.uint32))
+    scale = np.abs(m).max() * np.abs(v).max(axis=1, keepdims=True)
+    assert (np.abs(got - want) <= 4 * np.finfo(np.float32).eps * scale).all()
