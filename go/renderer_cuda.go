@@ -164,6 +164,15 @@ func (r *Renderer) optionBits() C.uint32_t {
 	if r.ShowTextures {
 		o |= C.GRB_OPT_SHOW_TEXTURES
 	}
+	if r.ShowEdges {
+		o |= C.GRB_OPT_SHOW_EDGES
+	}
+	if r.ShowVertices {
+		o |= C.GRB_OPT_SHOW_VERTICES
+	}
+	if !demoMode { // renderer.go:476-480
+		o |= C.GRB_OPT_CROSSHAIR
+	}
 	return o
 }
 

@@ -21,9 +21,14 @@ GRB_OPT_BACKFACE_CULLING = 1 << 2
 GRB_OPT_LIGHTING = 1 << 3
 GRB_OPT_FLAT_SHADING = 1 << 4
 GRB_OPT_SHOW_TEXTURES = 1 << 5
+GRB_OPT_SHOW_EDGES = 1 << 6
+GRB_OPT_SHOW_VERTICES = 1 << 7
+GRB_OPT_CROSSHAIR = 1 << 8
+GRB_OPT_FOG = 1 << 9
 GRB_OPT_DEFAULT = (GRB_OPT_FRUSTUM_CLIPPING | GRB_OPT_SHOW_FACES | GRB_OPT_BACKFACE_CULLING |
                    GRB_OPT_LIGHTING | GRB_OPT_SHOW_TEXTURES)
 GRB_TILE = 32
+GRB_ABI_VERSION = 2
 
 c_float_p = C.POINTER(C.c_float)
 c_i32_p = C.POINTER(C.c_int32)
@@ -48,6 +53,7 @@ class grb_draw_params(C.Structure):
         ("screen", C.c_float * 16), ("light", C.c_float * 3), ("options", C.c_uint32),
         ("z_near", C.c_float), ("z_far", C.c_float), ("ref_tiles", C.c_int32),
         ("row_begin", C.c_int32), ("row_end", C.c_int32),
+        ("fog_start", C.c_float), ("fog_end", C.c_float), ("fog_color", C.c_uint8 * 4),
     ]
 
 
@@ -144,7 +150,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.grb_abi_version() != 1:
+    if lib.grb_abi_version() != GRB_ABI_VERSION:
         raise ImportError("libgorender_b200.so ABI version mismatch")
     _lib = lib
     return lib

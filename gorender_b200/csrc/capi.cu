@@ -93,6 +93,7 @@ struct grb_context {
     DevBuf<TileDesc> desc;
     DevBuf<OverflowDesc> overflow;
     DevBuf<FrameCounters> counters;
+    DevBuf<unsigned long long> ovl;  // per-pixel overlay event keys (ShowEdges / ShowVertices draws only)
     uint32_t recCap = 0;  // per frame
 
     // last draw (for stats / debug read-backs)
@@ -355,6 +356,10 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     if (ctx->stageCapture)
         if (int32_t r = ensure(ctx, ctx->warpCount, F * std::max(ctx->nFaceBlocks, 1) * kWarpsPerFaceBlock, false)) return r;
     if (int32_t r = ensure(ctx, ctx->counters, F, false)) return r;
+    const bool overlayKeys = (prm->options & kOptOverlayKeys) != 0;
+    const size_t npix = (size_t)fb->width * fb->height;
+    if (overlayKeys)
+        if (int32_t r = ensure(ctx, ctx->ovl, F * npix, false)) return r;
     ctx->recCap = recCap;
     // per-tile descriptor counters must be zero on entry; the raster kernel re-zeroes what it
     // consumed, but the per-frame stride depends on nTiles (and a strip draw leaves the other
@@ -367,6 +372,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     CK(ctx, cudaMemcpyAsync(ctx->dFrameObjs.p, hfo, nfo * sizeof(FrameObj), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaEventRecord(ctx->stagingDone[ring], ctx->stream));
     CK(ctx, cudaMemsetAsync(ctx->counters.p, 0, F * sizeof(FrameCounters), ctx->stream));
+    if (overlayKeys) CK(ctx, cudaMemsetAsync(ctx->ovl.p, 0, F * npix * sizeof(unsigned long long), ctx->stream));
 
     DrawArgs a{};
     a.meshes = ctx->dMeshes.p;
@@ -391,6 +397,10 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.bigList = ctx->bigList.p;
     a.counters = ctx->counters.p;
     a.recCap = recCap;
+    a.ovl = overlayKeys ? ctx->ovl.p : nullptr;
+    a.fogStart = prm->fog_start;
+    a.fogEnd = prm->fog_end;
+    a.fogColor = make_uchar4(prm->fog_color[0], prm->fog_color[1], prm->fog_color[2], prm->fog_color[3]);
     a.color = fb->color + (size_t)frame0 * fb->width * fb->height;
     a.depth = fb->depth + (size_t)frame0 * fb->width * fb->height;
     a.width = fb->width;

@@ -13,6 +13,7 @@
 //   overflow  [frames][kMaxBinsPerTri*recCap] OverflowDesc  descriptors beyond descCap (rare)
 //   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles
 //   counters  [frames]                    FrameCounters
+//   ovl       [frames][H*W]               u64      overlay events (ShowEdges / ShowVertices only), see OverlayKey
 #pragma once
 
 #include <stdint.h>
@@ -109,6 +110,18 @@ struct __align__(16) FrameCounters {
     unsigned long long pad2;
 };
 
+// Overlays (drawProjection's ShowEdges / ShowVertices branches, renderer.go:191-216) are written
+// with FrameBuffer.Pixel — no depth test, not clipped to the tile — by every tile pass that lists
+// the triangle, so what a pixel finally shows is decided by the LAST write in the reference's
+// serial order: tile pass, then list position, then face < edges/centre mark < vertex marks.  Every
+// overlay pixel is recorded as max(event key) per pixel and the raster kernel's shading phase
+// compares it with the key of the pixel's last face write (its owning tile pass, winning slot).
+//   key = (tile pass + 1) << 34 | (record slot + 1) << 2 | kind      (0 = no overlay)
+constexpr int kOvlTileShift = 34, kOvlSlotShift = 2;
+constexpr unsigned long long kOvlKindEdge = 0ull, kOvlKindVertex = 1ull;
+constexpr uint32_t kOptOverlayKeys = GRB_OPT_SHOW_EDGES | GRB_OPT_SHOW_VERTICES;
+constexpr uint32_t kOptPostPass = kOptOverlayKeys | GRB_OPT_CROSSHAIR | GRB_OPT_FOG;
+
 struct RefTiles {            // the reference's tile grid (renderer.go:50-76)
     int32_t ntx, nty;        // numTilesX, numTilesY
     int32_t tw, th;          // tileWidth, tileHeight
@@ -137,6 +150,7 @@ struct DrawArgs {
     uint32_t *bigList;
     FrameCounters *counters;
     uint32_t recCap;
+    unsigned long long *ovl;    // null unless ShowEdges / ShowVertices
     // target
     uchar4 *color;              // [frames][H][W]
     float *depth;               // [frames][H][W]
@@ -150,6 +164,8 @@ struct DrawArgs {
     uint32_t options;
     float zNear, zFar;
     RefTiles ref;
+    float fogStart, fogEnd;     // FrameBuffer.Fog arguments (rasterizer.go:193), GRB_OPT_FOG only
+    uchar4 fogColor;
 };
 
 }  // namespace gr

@@ -197,6 +197,66 @@ __device__ __forceinline__ void write_quad(const DrawArgs &a, int frame, int gx,
     }
 }
 
+// ---- overlays and post passes (POST instantiation of the raster kernel only) -----------------
+//
+// drawProjection's ShowEdges / ShowVertices writes (renderer.go:191-216) arrive as one event key
+// per pixel from the setup kernel (gr_types.cuh, OverlayKey); the pixel's last FACE write happens
+// in the pass of the reference tile that owns it, at the winning triangle's list position
+// (DESIGN.md §4.3), so the overlay shows iff its key is not older than (owning tile, winner slot):
+// a triangle's own edges are drawn right after its face.  Then Draw's post passes in reference
+// order: CrossHair, Fog (renderer.go:476-480).  slot1[k] = winner slot + 1, 0 = no face.
+__device__ __forceinline__ void post_quad(const DrawArgs &a, int frame, int gx, int gy, uchar4 col[4], const float zo[4],
+                                          const uint32_t slot1[4]) {
+    const long long npix = (long long)a.width * a.height;
+    const long long idx0 = (long long)gy * a.width + gx;
+    if (a.ovl != nullptr) {
+        const unsigned long long *ovl = a.ovl + (size_t)frame * npix + idx0;
+        const int trow = min(gy / a.ref.th, a.ref.nty - 1) * a.ref.ntx;
+        const uchar4 edgeCol = (a.options & GRB_OPT_SHOW_FACES) ? make_uchar4(0, 0, 0, 255)         // edgeColor, renderer.go:19
+                                                                : make_uchar4(255, 255, 255, 255);  // renderer.go:193-196
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (gx + k >= a.width) break;
+            const unsigned long long ok = __ldg(ovl + k);
+            if (ok == 0) continue;
+            const int tile = trow + min((gx + k) / a.ref.tw, a.ref.ntx - 1);
+            const unsigned long long faceKey =
+                slot1[k] ? ((unsigned long long)(tile + 1) << kOvlTileShift) | ((unsigned long long)slot1[k] << kOvlSlotShift) : 0ull;
+            if (ok >= faceKey) col[k] = (ok & 1ull) ? make_uchar4(255, 161, 0, 255) : edgeCol;  // vertexColor, renderer.go:18
+        }
+    }
+    if (a.options & GRB_OPT_CROSSHAIR) {
+        // rasterizer.go:209-217: four 3-pixel axis-aligned lines around (W/2, H/2); Pixel() checks
+        // the linear index only, so the test is on the index distance from the centre
+        const long long c0 = (long long)(a.height / 2) * a.width + a.width / 2;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const long long idx = idx0 + k;
+            if (gx + k >= a.width || idx <= 0) continue;
+            const long long d = idx - c0, ad = d < 0 ? -d : d;
+            const bool horizontal = ad >= 3 && ad <= 5;
+            const bool vertical = ad % a.width == 0 && ad / a.width >= 3 && ad / a.width <= 5;
+            if (horizontal || vertical) col[k] = make_uchar4(255, 255, 0, 255);
+        }
+    }
+    if (a.options & GRB_OPT_FOG) {
+        // rasterizer.go:185-207
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float depth = zo[k];
+            if (depth >= a.fogStart) continue;
+            if (depth <= a.fogEnd) { col[k] = a.fogColor; continue; }
+            const float f = fsub(1.0f, fdiv(fsub(a.fogEnd, depth), fsub(a.fogEnd, a.fogStart)));
+            const float g = fsub(1.0f, f);
+            const uchar4 c = col[k], fc = a.fogColor;
+            col[k] = make_uchar4(go_u8(fadd(fmul((float)c.x, g), fmul((float)fc.x, f))),
+                                 go_u8(fadd(fmul((float)c.y, g), fmul((float)fc.y, f))),
+                                 go_u8(fadd(fmul((float)c.z, g), fmul((float)fc.z, f))),
+                                 go_u8(fadd(fmul((float)c.w, g), fmul((float)fc.w, f))));
+        }
+    }
+}
+
 // One batch of up to 32 list entries of a warp: lane `lane` holds record slot `slot` when
 // `have`.  Small triangles go through the coarse / fine stages; a large one (more than kSmallArea
 // pixels inside the tile) is swept by the whole warp, one tile row at a time, lane = column.
@@ -362,6 +422,8 @@ __device__ __forceinline__ void coop_pass(const uint32_t *largeQ, int nq, const 
     keys[py * kTile + px + 2] = k2; keys[py * kTile + px + 3] = k3;
 }
 
+// POST: the instantiation that also composes the overlays and runs the post passes (post_quad).
+template <bool POST>
 __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_kernel(const __grid_constant__ DrawArgs a) {
     __shared__ unsigned long long keys[kTilePix];
     __shared__ WarpTris tris[kRasterThreads / 32];
@@ -415,6 +477,10 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
             for (int k = 0; k < 4; k++) {
                 col[k] = background(dots, k);
                 zo[k] = -1.0f;
+            }
+            if constexpr (POST) {
+                const uint32_t none[4] = {0u, 0u, 0u, 0u};
+                post_quad(a, frame, gx, gy, col, zo, none);
             }
             write_quad(a, frame, gx, gy, col, zo);
         }
@@ -532,12 +598,14 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     TriRec r;
     Edges e;
     uint32_t have = 0;  // slot + 1 of the record held in r / e
+    uint32_t winner[4];
     const unsigned dots = dot_mask(gx, gy);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int x = gx + k;
         const unsigned long long key = keys[py * kTile + px + k];
         const uint32_t slot1 = (uint32_t)key;
+        winner[k] = slot1;
         if (slot1 == 0) {
             col[k] = background(dots, k);
             zo[k] = -1.0f;
@@ -580,6 +648,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                              go_u8(fmul((float)c.z, intensity)), c.w);
         zo[k] = z;
     }
+    if constexpr (POST) post_quad(a, frame, gx, gy, col, zo, winner);
     write_quad(a, frame, gx, gy, col, zo);
     }
 }
@@ -587,7 +656,10 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
 void launch_raster(const DrawArgs &a, int nframes, cudaStream_t s) {
     const int rows = a.tileRowEnd - a.tileRowBegin;
     if (rows <= 0 || a.ntx <= 0) return;
-    raster_kernel<<<dim3(a.ntx, rows, nframes), kRasterThreads, 0, s>>>(a);
+    if (a.options & kOptPostPass)
+        raster_kernel<true><<<dim3(a.ntx, rows, nframes), kRasterThreads, 0, s>>>(a);
+    else
+        raster_kernel<false><<<dim3(a.ntx, rows, nframes), kRasterThreads, 0, s>>>(a);
 }
 
 }  // namespace gr

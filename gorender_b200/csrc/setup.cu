@@ -166,15 +166,70 @@ struct Emit {
     int tpf;        // number of reference tile lists this triangle is in
     bool valid;     // gets a record (non-empty raster bbox, ShowFaces)
     bool bad;       // out of the integer domain
+    // overlay instantiation only
+    bool listed;    // in at least one reference tile list, with snapped coordinates in rec
+    int tmax;       // the last reference tile pass that lists it
+    int ccx, ccy;   // int(center.X), int(center.Y) of the face-centre mark (renderer.go:203-208)
 };
 
+// ---- overlays: FrameBuffer.Pixel / Rect / Line (rasterizer.go:25-30, 54-79) as per-pixel event keys
+
+// Pixel: the reference bounds-checks the LINEAR index only (0 < idx < len), so x outside the row
+// wraps into the neighbouring row and pixel 0 is never written.
+__device__ __forceinline__ void ovl_pixel(unsigned long long *ovl, long long x, long long y, int width, long long npix,
+                                          unsigned long long key) {
+    const long long idx = y * width + x;
+    if (idx > 0 && idx < npix) atomicMax(ovl + idx, key);
+}
+__device__ __forceinline__ void ovl_rect3(unsigned long long *ovl, int x, int y, int width, int height, long long npix,
+                                          unsigned long long key) {
+    if (x >= width || y >= height) return;
+    for (int py = y; py < y + 3; py++)
+        for (int px = x; px < x + 3; px++) ovl_pixel(ovl, px, py, width, npix, key);
+}
+// DDA with float32 steps accumulated by repeated addition: inherently serial per line.
+__device__ __forceinline__ void ovl_line(unsigned long long *ovl, int x0, int y0, int x1, int y1, int width, long long npix,
+                                         unsigned long long key) {
+    const int dx = x1 - x0, dy = y1 - y0;
+    const int side = max(abs(dx), abs(dy));
+    const float xs = fdiv((float)dx, (float)side), ys = fdiv((float)dy, (float)side);
+    float cx = (float)x0, cy = (float)y0;
+    for (int i = 0; i <= side; i++) {
+        // |cx|, |cy| stay within the snapped-coordinate domain: plain truncation == Go's int()
+        ovl_pixel(ovl, __float2int_rz(cx), __float2int_rz(cy), width, npix, key);
+        cx = fadd(cx, xs);
+        cy = fadd(cy, ys);
+    }
+}
+// drawProjection's overlay branches (renderer.go:191-216) for one listed triangle.
+__device__ __forceinline__ void draw_overlays(const DrawArgs &a, int frame, const TriRec &t, int tmax, int ccx, int ccy,
+                                              uint32_t slot) {
+    const long long npix = (long long)a.width * a.height;
+    unsigned long long *ovl = a.ovl + (size_t)frame * npix;
+    const unsigned long long base =
+        ((unsigned long long)(tmax + 1) << kOvlTileShift) | ((unsigned long long)(slot + 1u) << kOvlSlotShift);
+    if (a.options & GRB_OPT_SHOW_EDGES) {
+        ovl_line(ovl, t.x0, t.y0, t.x1, t.y1, a.width, npix, base | kOvlKindEdge);
+        ovl_line(ovl, t.x1, t.y1, t.x2, t.y2, a.width, npix, base | kOvlKindEdge);
+        ovl_line(ovl, t.x2, t.y2, t.x0, t.y0, a.width, npix, base | kOvlKindEdge);
+        if (a.options & GRB_OPT_SHOW_FACES) ovl_rect3(ovl, ccx - 1, ccy - 1, a.width, a.height, npix, base | kOvlKindEdge);
+    }
+    if (a.options & GRB_OPT_SHOW_VERTICES) {
+        ovl_rect3(ovl, t.x0 - 1, t.y0 - 1, a.width, a.height, npix, base | kOvlKindVertex);
+        ovl_rect3(ovl, t.x1 - 1, t.y1 - 1, a.width, a.height, npix, base | kOvlKindVertex);
+        ovl_rect3(ovl, t.x2 - 1, t.y2 - 1, a.width, a.height, npix, base | kOvlKindVertex);
+    }
+}
+
 // Everything between the clipper and the rasteriser for one output triangle.
+template <bool OVL>
 __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0, ScreenVert s1, ScreenVert s2,
                                                float i0, float i1, float i2, int tex) {
     Emit e;
     e.valid = false;
     e.bad = false;
     e.tpf = 0;
+    e.listed = false;
 
     // identifyTriangleTiles (renderer.go:226-244) on the float screen points
     // Go's min/max propagate NaN (then every tile comparison below is false): one check up front
@@ -200,7 +255,8 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
         if (maxY >= sy && minY <= ey) { nr++; r0 = min(r0, r); r1 = max(r1, r); }
     }
     e.tpf = nc * nr;
-    if (e.tpf == 0 || !(a.options & GRB_OPT_SHOW_FACES)) return e;
+    if (e.tpf == 0) return e;
+    if (!OVL && !(a.options & GRB_OPT_SHOW_FACES)) return e;
 
     bool bad = false;
     TriRec &t = e.rec;
@@ -208,6 +264,14 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
     t.x1 = snap(s1.sx, bad); t.y1 = snap(s1.sy, bad);
     t.x2 = snap(s2.sx, bad); t.y2 = snap(s2.sy, bad);
     if (bad) { e.bad = true; return e; }
+    if constexpr (OVL) {
+        e.listed = true;
+        e.tmax = r1 * a.ref.ntx + c1;   // tile index = row * numTilesX + column (renderer.go:62-63)
+        // renderer.go:203-208: centre of the float screen points, then int() - 1
+        e.ccx = __float2int_rz(fdiv(fadd(fadd(s0.sx, s1.sx), s2.sx), 3.0f));
+        e.ccy = __float2int_rz(fdiv(fadd(fadd(s0.sy, s1.sy), s2.sy), 3.0f));
+        if (!(a.options & GRB_OPT_SHOW_FACES)) return e;
+    }
     t.w0 = s0.w; t.w1 = s1.w; t.w2 = s2.w;
     t.i0 = i0; t.i1 = i1; t.i2 = i2;
     t.tex = tex;
@@ -294,8 +358,10 @@ struct __align__(16) StagedFace {
     float4 v0, v1, v2;       // clip-space vertices
 };
 
-template <bool CLIP>
-__global__ void __launch_bounds__(kFaceBlock, 5) setup_kernel(const __grid_constant__ DrawArgs a) {
+// OVL: the instantiation that also draws the ShowEdges / ShowVertices overlays (as event keys into
+// a.ovl); the frame path proper is the OVL = false one.
+template <bool CLIP, bool OVL>
+__global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : 5) setup_kernel(const __grid_constant__ DrawArgs a) {
     const int frame = blockIdx.y;
     const int fb = blockIdx.x;
     const int o = a.fblkObj[fb];
@@ -417,10 +483,12 @@ __global__ void __launch_bounds__(kFaceBlock, 5) setup_kernel(const __grid_const
         Emit e;
         e.valid = false;
         if (alive) {
-            e = setup_triangle(a, to_screen(a.screen, v0), to_screen(a.screen, v1), to_screen(a.screen, v2), in0, in1,
-                               in2, tex);
+            e = setup_triangle<OVL>(a, to_screen(a.screen, v0), to_screen(a.screen, v1), to_screen(a.screen, v2), in0,
+                                    in1, in2, tex);
             tpf = e.tpf;
             nbad = e.bad ? 1 : 0;
+            if constexpr (OVL)
+                if (e.listed) draw_overlays(a, frame, e.rec, e.tmax, e.ccx, e.ccy, slot);
         }
         const unsigned validMask = __ballot_sync(0xffffffffu, e.valid);
         emitted = __popc(validMask);
@@ -452,6 +520,7 @@ __global__ void __launch_bounds__(kFaceBlock, 5) setup_kernel(const __grid_const
         ScreenVert sv[9];
         int count = 0;
         unsigned validBits = 0;
+        int nRaster = 0;   // triangles of this lane that reach the rasteriser
         if (alive) {
             poly[0] = {v0, fuv.u0, fuv.v0, in0};
             poly[1] = {v1, fuv.u1, fuv.v1, in1};
@@ -461,11 +530,13 @@ __global__ void __launch_bounds__(kFaceBlock, 5) setup_kernel(const __grid_const
             for (int i = 0; i < count; i++) sv[i] = to_screen(a.screen, poly[i].p);
             // fan (0, i+1, i+2)  (clipping.go:54-59)
             for (int i = 0; i + 2 < count; i++) {
-                const Emit e = setup_triangle(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in,
-                                              poly[i + 2].in, tex);
+                const Emit e = setup_triangle<OVL>(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in,
+                                                   poly[i + 2].in, tex);
                 tpf += e.tpf;
                 nbad += e.bad ? 1 : 0;
-                if (e.valid) validBits |= 1u << i;
+                // with overlays every listed triangle takes a slot (its place in the serial order)
+                if (OVL ? e.listed : e.valid) validBits |= 1u << i;
+                nRaster += e.valid ? 1 : 0;
             }
         }
         // exclusive scan of the per-lane triangle counts over the warp
@@ -476,11 +547,21 @@ __global__ void __launch_bounds__(kFaceBlock, 5) setup_kernel(const __grid_const
             const int t = __shfl_up_sync(0xffffffffu, inc, d);
             if ((int)lane >= d) inc += t;
         }
-        emitted = (uint32_t)__shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t slotsUsed = (uint32_t)__shfl_sync(0xffffffffu, inc, 31);
+        emitted = OVL ? __reduce_add_sync(0xffffffffu, (uint32_t)nRaster) : slotsUsed;
         slot = slot0 + (uint32_t)(inc - mine);
         for (int i = 0; i + 2 < count; i++) {
             if (!(validBits & (1u << i))) continue;
-            Emit e = setup_triangle(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in, poly[i + 2].in, tex);
+            Emit e = setup_triangle<OVL>(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in, poly[i + 2].in, tex);
+            if constexpr (OVL) {
+                draw_overlays(a, frame, e.rec, e.tmax, e.ccx, e.ccy, slot);
+                if (!e.valid) {
+                    // keeps its slot for the order, draws no face: empty bbox for the stage read-back
+                    if (a.warpCount) reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot)[3] = make_int4(1, 0, -1, 0);
+                    slot++;
+                    continue;
+                }
+            }
             const TriUV uv = {poly[0].u, poly[0].v, poly[i + 1].u, poly[i + 1].v, poly[i + 2].u, poly[i + 2].v};
             const TileSpan sp = tile_span(e.rec);
             const bool big = sp.count() > kMaxBinsPerTri;
@@ -490,7 +571,7 @@ __global__ void __launch_bounds__(kFaceBlock, 5) setup_kernel(const __grid_const
             if (big || sp.count() > 1) bin_other_tiles(a, frame, sp, slot);
             slot++;
         }
-        if (lane == 0 && a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = emitted;
+        if (lane == 0 && a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = slotsUsed;
     }
 
     // TPF (renderer.go:436-441) and diagnostics: one atomic per warp
@@ -514,8 +595,14 @@ void launch_transform(const DrawArgs &a, int nframes, cudaStream_t s) {
 
 void launch_setup(const DrawArgs &a, int nframes, bool anyPlain, bool anyClip, cudaStream_t s) {
     if (a.nFaceBlocks == 0) return;
-    if (anyPlain) setup_kernel<false><<<dim3(a.nFaceBlocks, nframes), kFaceBlock, 0, s>>>(a);
-    if (anyClip) setup_kernel<true><<<dim3(a.nFaceBlocks, nframes), kFaceBlock, 0, s>>>(a);
+    const dim3 grid(a.nFaceBlocks, nframes);
+    if (a.ovl != nullptr) {
+        if (anyPlain) setup_kernel<false, true><<<grid, kFaceBlock, 0, s>>>(a);
+        if (anyClip) setup_kernel<true, true><<<grid, kFaceBlock, 0, s>>>(a);
+    } else {
+        if (anyPlain) setup_kernel<false, false><<<grid, kFaceBlock, 0, s>>>(a);
+        if (anyClip) setup_kernel<true, false><<<grid, kFaceBlock, 0, s>>>(a);
+    }
 }
 
 void launch_matvec_batch(const float m[16], float4 *vecs, long long n, cudaStream_t s) {

@@ -32,6 +32,8 @@ static void printMatrix(const char *name, const Matrix &m) {
 int main(int argc, char **argv) {
     int width = 1280, height = 720, frames = 100, start = 0;
     bool matricesOnly = false, texDump = false, async = false;
+    // the option hot-keys of main.go:255-272 as flags
+    bool edges = false, vertices = false, noFaces = false, crossHair = false, noCull = false, noLight = false, flat = false;
     std::string ppm, raw, file;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -45,6 +47,13 @@ int main(int argc, char **argv) {
         else if (a == "-matrices") matricesOnly = true;
         else if (a == "-texdump") texDump = true;
         else if (a == "-async") async = true;
+        else if (a == "-edges") edges = true;
+        else if (a == "-vertices") vertices = true;
+        else if (a == "-nofaces") noFaces = true;
+        else if (a == "-crosshair") crossHair = true;
+        else if (a == "-nocull") noCull = true;
+        else if (a == "-nolight") noLight = true;
+        else if (a == "-flat") flat = true;
         else file = a;
     }
     if (file.empty()) {
@@ -86,6 +95,13 @@ int main(int argc, char **argv) {
         Device dev(0);
         FrameBuffer fb(dev, width, height);
         Renderer renderer(fb);
+        renderer.ShowEdges = edges;
+        renderer.ShowVertices = vertices;
+        renderer.ShowFaces = !noFaces;
+        renderer.CrossHair = crossHair;
+        renderer.BackfaceCulling = !noCull;
+        renderer.Lighting = !noLight;
+        renderer.FlatShading = flat;
         const auto t0 = std::chrono::steady_clock::now();
         if (async) {
             // main.go:198-227 with the present step replaced by "the frame is in Pixels2"

@@ -638,6 +638,11 @@ class Renderer {  // renderer.go:83-164
 public:
     bool FrustumClipping = true, ShowVertices = false, ShowEdges = false, ShowFaces = true, BackfaceCulling = true,
          Lighting = true, FlatShading = false, ShowTextures = true;  // renderer.go:130-137
+    // renderer.go:476-480: `if !demoMode { CrossHair; // Fog(0.100, 0.033, {100,100,100,255}) }` —
+    // compile-time switches in the reference (main.go:22), run-time fields here
+    bool CrossHair = false, Fog = false;
+    float FogStart = 0.100f, FogEnd = 0.033f;
+    uint8_t FogColor[4] = {100, 100, 100, 255};
     int TPF = 0;
 
     explicit Renderer(FrameBuffer &fb, bool parallel = true) : fb_(fb) {
@@ -655,6 +660,10 @@ public:
         if (Lighting) o |= GRB_OPT_LIGHTING;
         if (FlatShading) o |= GRB_OPT_FLAT_SHADING;
         if (ShowTextures) o |= GRB_OPT_SHOW_TEXTURES;
+        if (ShowEdges) o |= GRB_OPT_SHOW_EDGES;
+        if (ShowVertices) o |= GRB_OPT_SHOW_VERTICES;
+        if (CrossHair) o |= GRB_OPT_CROSSHAIR;
+        if (Fog) o |= GRB_OPT_FOG;
         return o;
     }
 
@@ -709,6 +718,8 @@ private:
         p.options = options();
         p.z_near = zNear_; p.z_far = zFar_;
         p.ref_tiles = numTiles_;
+        p.fog_start = FogStart; p.fog_end = FogEnd;
+        std::memcpy(p.fog_color, FogColor, 4);
     }
 
     FrameBuffer &fb_;

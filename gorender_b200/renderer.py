@@ -268,6 +268,12 @@ class Renderer:
         self.TPF = 0
         self.DebugEnabled = False
         self.DebugInfo: list = []
+        # renderer.go:476-480: `if !demoMode { CrossHair; // Fog(0.100, 0.033, {100,100,100,255}) }` —
+        # compile-time switches in the reference (main.go:22), run-time fields here
+        self.CrossHair = False
+        self.Fog = False
+        self.FogStart, self.FogEnd = np.float32(0.100), np.float32(0.033)
+        self.FogColor = (100, 100, 100, 255)
         # renderer.go:144,151: numTiles is 1 when !parallel, else max(NumCPU, 16) (16 on any
         # host the reference runs on: more than 16 CPUs panic)
         self.numTiles = 16 if parallel else 1
@@ -282,10 +288,15 @@ class Renderer:
         if self.Lighting: o |= _cabi.GRB_OPT_LIGHTING
         if self.FlatShading: o |= _cabi.GRB_OPT_FLAT_SHADING
         if self.ShowTextures: o |= _cabi.GRB_OPT_SHOW_TEXTURES
+        if self.ShowEdges: o |= _cabi.GRB_OPT_SHOW_EDGES
+        if self.ShowVertices: o |= _cabi.GRB_OPT_SHOW_VERTICES
+        if self.CrossHair: o |= _cabi.GRB_OPT_CROSSHAIR
+        if self.Fog: o |= _cabi.GRB_OPT_FOG
         return o
 
     def draw_params(self, rows: Optional[Tuple[int, int]] = None) -> _cabi.grb_draw_params:
-        key = (rows, self.options(), self.numTiles, float(self.zNear), float(self.zFar), self.fb.Width, self.fb.Height)
+        key = (rows, self.options(), self.numTiles, float(self.zNear), float(self.zFar), self.fb.Width, self.fb.Height,
+               float(self.FogStart), float(self.FogEnd), tuple(self.FogColor))
         cached = getattr(self, "_params_cache", None)
         if cached is not None and cached[0] == key:
             return cached[1]
@@ -303,6 +314,8 @@ class Renderer:
         p.z_near, p.z_far = float(self.zNear), float(self.zFar)
         p.ref_tiles = self.numTiles
         p.row_begin, p.row_end = (rows if rows is not None else (0, 0))
+        p.fog_start, p.fog_end = float(self.FogStart), float(self.FogEnd)
+        p.fog_color = (C.c_uint8 * 4)(*[int(c) & 0xff for c in self.FogColor])
         return p
 
     def perspective(self) -> np.ndarray:

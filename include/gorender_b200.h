@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GRB_ABI_VERSION 1
+#define GRB_ABI_VERSION 2
 
 enum {
     GRB_OK = 0,
@@ -51,6 +51,14 @@ enum {
     GRB_OPT_LIGHTING         = 1u << 3,
     GRB_OPT_FLAT_SHADING     = 1u << 4,
     GRB_OPT_SHOW_TEXTURES    = 1u << 5,
+    /* Overlays of drawProjection (renderer.go:191-216): wireframe edges + face-centre marks
+     * (FrameBuffer.Line / Rect, rasterizer.go:54-79) and 3x3 vertex marks. */
+    GRB_OPT_SHOW_EDGES       = 1u << 6,
+    GRB_OPT_SHOW_VERTICES    = 1u << 7,
+    /* Post passes of Draw (renderer.go:476-480).  The reference compiles them in or out
+     * (`!demoMode`, main.go:22; the Fog call is commented out); here they are option bits. */
+    GRB_OPT_CROSSHAIR        = 1u << 8,   /* FrameBuffer.CrossHair({255,255,0,255}), rasterizer.go:209-217 */
+    GRB_OPT_FOG              = 1u << 9,   /* FrameBuffer.Fog(fog_start, fog_end, fog_color), rasterizer.go:193-207 */
     GRB_OPT_DEFAULT = GRB_OPT_FRUSTUM_CLIPPING | GRB_OPT_SHOW_FACES |
                       GRB_OPT_BACKFACE_CULLING | GRB_OPT_LIGHTING |
                       GRB_OPT_SHOW_TEXTURES
@@ -98,6 +106,8 @@ typedef struct grb_draw_params {
                                 TPF and the tile-list membership rule (renderer.go:226-244) */
     int32_t row_begin;       /* sort-first strip: rasterise rows [row_begin,row_end); */
     int32_t row_end;         /*   both multiples of GRB_TILE; 0,0 = whole frame       */
+    float fog_start, fog_end;/* GRB_OPT_FOG: Fog(fogStart, fogEnd, c); renderer.go:479 has 0.100, 0.033 */
+    uint8_t fog_color[4];    /*   ... and {100,100,100,255}                                */
 } grb_draw_params;
 
 #define GRB_TILE 32          /* device raster tile edge, pixels */

@@ -384,7 +384,9 @@ RGBA texture_sample(const orc_texture &t, float u, float v) {
 
 // ------------------------------------------------------------ rasterizer.go
 
-constexpr RGBA kFaceColor{200, 200, 200, 255};  // renderer.go:17
+constexpr RGBA kFaceColor{200, 200, 200, 255};    // renderer.go:17
+constexpr RGBA kVertexColor{255, 161, 0, 255};    // renderer.go:18
+constexpr RGBA kEdgeColor{0, 0, 0, 255};          // renderer.go:19
 
 struct FrameBuffer {
     int width = 0, height = 0;
@@ -404,6 +406,59 @@ struct FrameBuffer {
                 int64_t idx = (int64_t)y * width + x;
                 if (idx > 0 && idx < (int64_t)pix.size()) pix[idx] = c;
             }
+    }
+    // rasterizer.go:25-30: bounds are checked on the LINEAR index only, so x outside [0, width)
+    // wraps into the neighbouring row, and index 0 is never written
+    void pixel(int64_t x, int64_t y, RGBA c) {
+        // y * width + x in wrapping int64 arithmetic, like Go
+        const int64_t idx = (int64_t)((uint64_t)y * (uint64_t)width + (uint64_t)x);
+        if (idx > 0 && idx < (int64_t)pix.size()) pix[idx] = c;
+    }
+    // rasterizer.go:54-63
+    void rect(int64_t x, int64_t y, int64_t w, int64_t h, RGBA c) {
+        if (x >= width || y >= height) return;
+        for (int64_t py = y; py < y + h; py++)
+            for (int64_t px = x; px < x + w; px++) pixel(px, py, c);
+    }
+    // rasterizer.go:65-79: DDA with float32 steps accumulated by repeated addition
+    void line(int64_t x0, int64_t y0, int64_t x1, int64_t y1, RGBA c) {
+        const int64_t dx = x1 - x0, dy = y1 - y0;
+        const int64_t side = std::max(dx < 0 ? -dx : dx, dy < 0 ? -dy : dy);
+        const float xs = (float)dx / (float)side, ys = (float)dy / (float)side;
+        float cx = (float)x0, cy = (float)y0;
+        for (int64_t i = 0; i <= side; i++) {
+            pixel(go_int(cx), go_int(cy), c);
+            cx += xs;
+            cy += ys;
+        }
+    }
+    // rasterizer.go:209-217
+    void cross_hair(RGBA c) {
+        const int64_t size = 5, offset = 3;
+        const int64_t x = width / 2, y = height / 2;
+        line(x - size, y, x - offset, y, c);
+        line(x + offset, y, x + size, y, c);
+        line(x, y - size, x, y - offset, c);
+        line(x, y + offset, x, y + size, c);
+    }
+    // rasterizer.go:185-191
+    static RGBA blend(RGBA a, RGBA b, float f) {
+        return {go_u8((float)a.r * (1 - f) + (float)b.r * f), go_u8((float)a.g * (1 - f) + (float)b.g * f),
+                go_u8((float)a.b * (1 - f) + (float)b.b * f), go_u8((float)a.a * (1 - f) + (float)b.a * f)};
+    }
+    // rasterizer.go:193-207
+    void fog(float fog_start, float fog_end, RGBA c) {
+        for (size_t i = 0; i < pix.size(); i++) {
+            const float depth = z[i];
+            if (depth >= fog_start) {
+                // noop
+            } else if (depth <= fog_end) {
+                pix[i] = c;
+            } else {
+                const float f = 1 - ((fog_end - depth) / (fog_end - fog_start));
+                pix[i] = blend(pix[i], c, f);
+            }
+        }
     }
 };
 
@@ -592,6 +647,9 @@ struct orc_renderer {
     M4 screen;
     V3 light;
     uint32_t options = 0;
+    // Fog arguments (the call is commented out at renderer.go:479 with 0.100, 0.033, {100,100,100,255})
+    float fog_start = 0.100f, fog_end = 0.033f;
+    RGBA fog_color{100, 100, 100, 255};
 };
 
 namespace {
@@ -747,22 +805,46 @@ void project_object(orc_renderer &r, int oi, const orc_object &obj, bool locked)
         }
 }
 
-// renderer.go:166-189 (ShowFaces branch only; overlays are out of scope) + :219-223
+// drawProjection (renderer.go:166-217) over the tile's list (renderTile, :219-223).  The overlays
+// (ShowEdges / ShowVertices) are drawn by every tile pass that lists the triangle, unclipped by the
+// tile and without a depth test, so the image depends on the serial order tile 0..15, list order
+// inside a tile, face -> edges -> centre mark -> vertex marks inside a triangle.
 template <bool kCount>
 void render_tile(orc_renderer &r, unsigned tile) {
     const TileBounds &b = r.bounds[tile];
     const bool show_tex = r.options & ORC_OPT_SHOW_TEXTURES;
-    if (!(r.options & ORC_OPT_SHOW_FACES)) return;
+    const bool show_faces = r.options & ORC_OPT_SHOW_FACES;
+    const bool show_edges = r.options & ORC_OPT_SHOW_EDGES;
+    const bool show_verts = r.options & ORC_OPT_SHOW_VERTICES;
+    if (!show_faces && !show_edges && !show_verts) return;
     for (const Triangle &t : r.tile_tris[tile]) {
-        const orc_texture *tex = nullptr;
-        if (show_tex && t.tex >= 0 && t.tex < r.ntex) tex = &r.textures[t.tex];
         const V4 &a = t.points[0], &bb = t.points[1], &c = t.points[2];
-        fb_triangle<kCount>(r.fb,
-                            go_int(a.x), go_int(a.y), a.w, t.uvs[0].u, t.uvs[0].v,
-                            go_int(bb.x), go_int(bb.y), bb.w, t.uvs[1].u, t.uvs[1].v,
-                            go_int(c.x), go_int(c.y), c.w, t.uvs[2].u, t.uvs[2].v,
-                            go_int(b.sx), go_int(b.sy), go_int(b.ex), go_int(b.ey),
-                            t.intensity[0], t.intensity[1], t.intensity[2], tex);
+        if (show_faces) {  // :180-189
+            const orc_texture *tex = nullptr;
+            if (show_tex && t.tex >= 0 && t.tex < r.ntex) tex = &r.textures[t.tex];
+            fb_triangle<kCount>(r.fb,
+                                go_int(a.x), go_int(a.y), a.w, t.uvs[0].u, t.uvs[0].v,
+                                go_int(bb.x), go_int(bb.y), bb.w, t.uvs[1].u, t.uvs[1].v,
+                                go_int(c.x), go_int(c.y), c.w, t.uvs[2].u, t.uvs[2].v,
+                                go_int(b.sx), go_int(b.sy), go_int(b.ex), go_int(b.ey),
+                                t.intensity[0], t.intensity[1], t.intensity[2], tex);
+        }
+        if (show_edges) {  // :191-210
+            RGBA colr = kEdgeColor;
+            if (!show_faces) colr = {255, 255, 255, 255};
+            r.fb.line(go_int(a.x), go_int(a.y), go_int(bb.x), go_int(bb.y), colr);
+            r.fb.line(go_int(bb.x), go_int(bb.y), go_int(c.x), go_int(c.y), colr);
+            r.fb.line(go_int(c.x), go_int(c.y), go_int(a.x), go_int(a.y), colr);
+            if (show_faces) {
+                const float cx = (a.x + bb.x + c.x) / 3, cy = (a.y + bb.y + c.y) / 3;
+                r.fb.rect(go_int(cx) - 1, go_int(cy) - 1, 3, 3, colr);
+            }
+        }
+        if (show_verts) {  // :212-216
+            r.fb.rect(go_int(a.x) - 1, go_int(a.y) - 1, 3, 3, kVertexColor);
+            r.fb.rect(go_int(bb.x) - 1, go_int(bb.y) - 1, 3, 3, kVertexColor);
+            r.fb.rect(go_int(c.x) - 1, go_int(c.y) - 1, 3, 3, kVertexColor);
+        }
     }
 }
 
@@ -786,6 +868,12 @@ orc_renderer *orc_renderer_create(int32_t width, int32_t height, int32_t num_til
 void orc_renderer_destroy(orc_renderer *r) { delete r; }
 
 void orc_renderer_record_triangles(orc_renderer *r, int32_t enable) { r->record = enable != 0; }
+
+void orc_renderer_set_fog(orc_renderer *r, float fog_start, float fog_end, const uint8_t color[4]) {
+    r->fog_start = fog_start;
+    r->fog_end = fog_end;
+    r->fog_color = {color[0], color[1], color[2], color[3]};
+}
 
 // renderer.go:443-483
 int32_t orc_renderer_draw(orc_renderer *r, const orc_mesh *meshes, int32_t nmesh,
@@ -822,6 +910,11 @@ int32_t orc_renderer_draw(orc_renderer *r, const orc_mesh *meshes, int32_t nmesh
         for (int i = 0; i < nobj; i++) project_object(*r, i, objects[i], false);
         for (unsigned t = 0; t < r->num_tiles; t++) render_tile<true>(*r, t);
     }
+
+    // :476-480 — `if !demoMode { CrossHair; // Fog }`: demoMode is a constant true in main.go:22
+    // and the Fog call is commented out, so both are option bits here
+    if (options & ORC_OPT_CROSSHAIR) r->fb.cross_hair({255, 255, 0, 255});
+    if (options & ORC_OPT_FOG) r->fb.fog(r->fog_start, r->fog_end, r->fog_color);
 
     // :436-441
     r->tpf = 0;

@@ -35,6 +35,10 @@ enum {
     ORC_OPT_LIGHTING         = 1u << 3,
     ORC_OPT_FLAT_SHADING     = 1u << 4,
     ORC_OPT_SHOW_TEXTURES    = 1u << 5,
+    ORC_OPT_SHOW_EDGES       = 1u << 6,   /* renderer.go:191-210 */
+    ORC_OPT_SHOW_VERTICES    = 1u << 7,   /* renderer.go:212-216 */
+    ORC_OPT_CROSSHAIR        = 1u << 8,   /* renderer.go:476-478 (`!demoMode`, a constant in main.go:22) */
+    ORC_OPT_FOG              = 1u << 9,   /* renderer.go:479 (commented out in the reference) */
     ORC_OPT_DEFAULT = ORC_OPT_FRUSTUM_CLIPPING | ORC_OPT_SHOW_FACES |
                       ORC_OPT_BACKFACE_CULLING | ORC_OPT_LIGHTING |
                       ORC_OPT_SHOW_TEXTURES /* renderer.go:130-137 */
@@ -94,6 +98,10 @@ void orc_renderer_destroy(orc_renderer *r);
 
 /* Keep a copy of every emitted triangle (submission order; serial mode only). */
 void orc_renderer_record_triangles(orc_renderer *r, int32_t enable);
+
+/* Arguments of FrameBuffer.Fog (rasterizer.go:193-207) used when ORC_OPT_FOG is set; the
+ * defaults are the ones of the commented-out call at renderer.go:479. */
+void orc_renderer_set_fog(orc_renderer *r, float fog_start, float fog_end, const uint8_t color[4]);
 
 /* Renderer.Draw (renderer.go:443-483).  Returns 0, or -1 on bad arguments. */
 int32_t orc_renderer_draw(orc_renderer *r,

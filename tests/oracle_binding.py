@@ -66,6 +66,7 @@ class Oracle:
         L.orc_renderer_create.argtypes = [C.c_int32] * 4
         L.orc_renderer_destroy.argtypes = [C.c_void_p]
         L.orc_renderer_record_triangles.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_renderer_set_fog.argtypes = [C.c_void_p, C.c_float, C.c_float, C.POINTER(C.c_uint8)]
         L.orc_renderer_draw.restype = C.c_int32
         L.orc_renderer_draw.argtypes = [C.c_void_p, C.POINTER(orc_mesh), C.c_int32, C.POINTER(orc_texture), C.c_int32,
                                         C.POINTER(orc_object), C.c_int32, c_float_p, c_float_p, C.c_uint32]
@@ -252,6 +253,9 @@ class Oracle:
         assert r
         try:
             self.lib.orc_renderer_record_triangles(r, int(record))
+            fog = (C.c_uint8 * 4)(*[int(c) & 0xff for c in getattr(renderer, "FogColor", (100, 100, 100, 255))])
+            self.lib.orc_renderer_set_fog(r, float(getattr(renderer, "FogStart", 0.100)),
+                                          float(getattr(renderer, "FogEnd", 0.033)), fog)
             rc = self.lib.orc_renderer_draw(r, m["meshes"], m["nmesh"], m["textures"], m["ntex"], m["objs"], m["nobj"],
                                             _fp(m["screen"]), _fp(m["light"]), m["options"])
             assert rc == 0

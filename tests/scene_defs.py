@@ -186,4 +186,22 @@ PINNED: Dict[str, Callable[[], SceneDef]] = {
     "big_triangles": big_triangles,
     "no_faces": lambda: c1(640, 360, ShowFaces=False),
     "no_clipping_inside": lambda: c1(640, 360, FrustumClipping=False),
+    # overlays and post passes (renderer.go:191-216, 476-480)
+    "wire_c1": lambda: c1(640, 360, ShowEdges=True),
+    "wire_only_c1": lambda: c1(640, 360, ShowEdges=True, ShowFaces=False),
+    "verts_c1": lambda: c1(640, 360, ShowVertices=True),
+    "verts_only_c1": lambda: c1(333, 211, ShowVertices=True, ShowFaces=False),
+    "wire_verts_c2A": lambda: c2("A", ShowEdges=True, ShowVertices=True),
+    "wire_c2B_serial": lambda: SceneDef(800, 600, *workloads.config_c2("B"), options=dict(ShowEdges=True), parallel=False),
+    "wire_verts_multi_object": lambda: multi_object(ShowEdges=True, ShowVertices=True),
+    "wire_verts_sphere_n20": lambda: c3(20, ShowEdges=True, ShowVertices=True),
+    "wire_inside_sphere": lambda: inside_sphere(ShowEdges=True, ShowVertices=True),
+    "wire_odd_size_crosshair": lambda: odd_size(ShowEdges=True, ShowVertices=True, CrossHair=True),
+    "wire_tiny_far": lambda: tiny_far(ShowEdges=True),
+    "crosshair_c1": lambda: c1(640, 360, CrossHair=True),
+    "crosshair_empty_tiny": lambda: empty_scene(7, 9, CrossHair=True),
+    "fog_tiny_far": lambda: tiny_far(Fog=True, CrossHair=True),
+    "fog_c1_custom": lambda: c1(640, 360, Fog=True, FogStart=np.float32(0.25), FogEnd=np.float32(0.17),
+                                FogColor=(10, 200, 90, 128)),
+    "fog_wire_gouraud": lambda: gouraud_sphere(ShowEdges=True, Fog=True, FogStart=np.float32(0.7), FogEnd=np.float32(0.4)),
 }

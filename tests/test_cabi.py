@@ -26,14 +26,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in gorender_b200.h but not exported"
     assert sorted(_cabi.SIGNATURES) == names, "ctypes signature table out of sync with the header"
-    assert lib.grb_abi_version() == 1
+    assert lib.grb_abi_version() == _cabi.GRB_ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_cabi.grb_object) == 4 + 64 + 64
     assert C.sizeof(_cabi.grb_triangle_rec) == 64
     assert C.sizeof(_cabi.grb_frame_stats) == 24
-    assert C.sizeof(_cabi.grb_draw_params) == 64 + 12 + 4 + 8 + 12
+    assert C.sizeof(_cabi.grb_draw_params) == 64 + 12 + 4 + 8 + 12 + 8 + 4
     assert _cabi.grb_mesh_desc.bbox.offset == 72 and C.sizeof(_cabi.grb_mesh_desc) == 72 + 128
 
 

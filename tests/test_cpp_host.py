@@ -129,3 +129,10 @@ def test_headless_driver_matches_python_path(tmp_path, device):
     raw2 = tmp_path / "out_async.bin"
     run("-w", 640, "-h", 360, "-frames", 3, "-async", "-raw", raw2, obj)
     assert np.array_equal(np.fromfile(raw2, dtype=np.uint8), blob)
+    # the option hot-keys (main.go:255-272) as flags: wireframe + vertex marks + crosshair
+    raw3 = tmp_path / "out_wire.bin"
+    run("-w", 640, "-h", 360, "-frames", 3, "-edges", "-vertices", "-crosshair", "-raw", raw3, obj)
+    r.ShowEdges = r.ShowVertices = r.CrossHair = True
+    r.Draw([o], geometry.default_camera())
+    wire = np.fromfile(raw3, dtype=np.uint8)[:640 * 360 * 4].reshape(360, 640, 4)
+    assert np.array_equal(wire, fb.Pixels) and not np.array_equal(wire, px)

@@ -63,6 +63,16 @@ def test_random_scene(seed, device, oracle):
     r.Lighting = bool(rng.random() < 0.8)
     r.FlatShading = bool(rng.random() < 0.3)
     r.ShowTextures = bool(rng.random() < 0.8)
+    # overlays / post passes on a third of the scenes (drawn after the other choices so that the
+    # scenes of the seeds without them stay what they were)
+    orng = np.random.default_rng(5000 + seed)
+    if seed % 3 == 2:
+        r.ShowEdges = bool(orng.random() < 0.7)
+        r.ShowVertices = bool(orng.random() < 0.6)
+        r.ShowFaces = bool(orng.random() < 0.7)
+        r.CrossHair = bool(orng.random() < 0.5)
+        r.Fog = bool(orng.random() < 0.4)
+        r.FogStart, r.FogEnd = np.float32(orng.uniform(0.3, 1.0)), np.float32(orng.uniform(0.05, 0.3))
     r.Draw(objs, cam)
     ref = oracle.draw(r, objs, cam)
     assert int(r.last_stats["out_of_domain"][0]) == 0

@@ -189,6 +189,46 @@ def test_strips_compose_to_full_frame(strips, device, oracle):
     assert_frame_equal(px, z, ref, f"{strips} strips")
 
 
+def test_strips_with_overlays(device, oracle):
+    """Overlay pixels cross strip borders (lines are not clipped to tiles): every rank draws all of
+    them and composes its own rows."""
+    sc = scene_defs.multi_object(ShowEdges=True, ShowVertices=True, CrossHair=True)
+    fb = g.FrameBuffer(sc.width, sc.height, 1, device)
+    r = sc.renderer(fb)
+    ref = oracle.draw(r, sc.objects, sc.camera)
+    packed = r.pack_objects(sc.objects, [sc.camera])
+    from gorender_b200.parallel import strip_rows
+
+    px = np.zeros((sc.height, sc.width, 4), np.uint8)
+    z = np.zeros((sc.height, sc.width), np.float32)
+    for k in range(3):
+        y0, y1 = strip_rows(sc.height, 3, k)
+        r.draw_packed(packed, 0, rows=(y0, y1))
+        p, zz = fb.read(0, 1)
+        px[y0:y1] = p[0, y0:y1]
+        z[y0:y1] = zz[0, y0:y1]
+    assert_frame_equal(px, z, ref, "3 strips with overlays")
+
+
+def test_overlay_batch(device, oracle):
+    """Overlays in a frame-parallel batch: per-frame event-key planes."""
+    objs, cam = workloads.config_c1()
+    rot = geometry.spin_rotations(4, start=10)
+    fb = g.FrameBuffer(640, 360, len(rot), device)
+    r = g.Renderer(fb)
+    r.ShowEdges = True
+    r.ShowVertices = True
+    px, z, tpf = r.DrawBatch(objs, [cam] * len(rot), rotations_y=rot)
+    for f in range(len(rot)):
+        ref = oracle.draw(r, objs, cam, rotation_y=rot[f])
+        assert int(tpf[f]) == ref["tpf"]
+        assert_frame_equal(px[f], z[f], ref, f"overlay batch frame {f}")
+    # and the plain path right after, on the same context (the overlay plane must not leak)
+    r.ShowEdges = r.ShowVertices = False
+    px, z, tpf = r.DrawBatch(objs, [cam] * len(rot), rotations_y=rot)
+    assert_frame_equal(px[1], z[1], oracle.draw(r, objs, cam, rotation_y=rot[1]), "plain after overlay")
+
+
 def test_full_size_properties_4k(device):
     """C4 at its BASELINE size (2M faces, 3840x2160) through size-independent properties:
     determinism, strip/full agreement, batch/single agreement, and depth-vs-colour consistency."""
