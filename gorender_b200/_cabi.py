@@ -105,6 +105,8 @@ SIGNATURES = {
     "grb_texture_upload": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_float, c_u8_p, _VP, c_i32_p]),
     "grb_texture_set_scale": (C.c_int32, [_VP, C.c_int32, C.c_float]),
     "grb_mesh_upload": (C.c_int32, [_VP, C.POINTER(grb_mesh_desc), c_i32_p]),
+    "grb_mesh_new": (C.c_int32, [_VP, C.POINTER(grb_mesh_desc), c_i32_p]),
+    "grb_mesh_read_derived": (C.c_int32, [_VP, C.c_int32, _VP, _VP]),
     "grb_mesh_free": (C.c_int32, [_VP, C.c_int32]),
     "grb_framebuffer_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_VP)]),
     "grb_framebuffer_wrap": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.POINTER(_VP)]),

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -622,19 +623,29 @@ int32_t grb_texture_set_scale(grb_context *ctx, int32_t id, float scale) {
     return GRB_OK;
 }
 
-int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_id) {
+}  // extern "C"
+
+namespace {
+
+template <typename T> int32_t dev_alloc(grb_context *ctx, size_t n, T **out, std::vector<void *> &allocs) {
+    *out = nullptr;
+    if (n == 0) return GRB_OK;
+    void *p = nullptr;
+    CK(ctx, cudaMalloc(&p, n * sizeof(T)));
+    allocs.push_back(p);
+    *out = static_cast<T *>(p);
+    return GRB_OK;
+}
+
+// Shared body of grb_mesh_upload / grb_mesh_new.  The source arrays go up as they are; everything
+// derived from them — the index check, the face-corner expansion the frame kernels stream and,
+// with `derive`, NewMesh's face normals and bounding box — is produced on the device (mesh.cu).
+int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, int32_t *out_id) {
     if (!ctx || !d || !out_id) return fail(ctx, GRB_ERR_INVALID, "null argument");
-    if (d->nv <= 0 || d->nf < 0 || d->nvn < 0 || !d->vertices || (d->nf > 0 && (!d->vidx || !d->fnormals)))
+    if (d->nv <= 0 || d->nf < 0 || d->nvn < 0 || !d->vertices || (d->nf > 0 && (!d->vidx || (!derive && !d->fnormals))))
         return fail(ctx, GRB_ERR_INVALID, "mesh needs vertices, face normals and vertex indices");
-    // the reference would panic on an out-of-range index (renderer.go:318-320, 328-330)
-    for (int64_t i = 0; i < (int64_t)d->nf * 3; i++)
-        if (d->vidx[i] < 0 || d->vidx[i] >= d->nv) return fail(ctx, GRB_ERR_INVALID, "vertex index out of range");
-    if (d->nvn > 0) {
-        if (!d->vnormals || !d->nidx) return fail(ctx, GRB_ERR_INVALID, "mesh with vertex normals needs normal indices");
-        for (int64_t i = 0; i < (int64_t)d->nf * 3; i++)
-            if (d->nidx[i] < 0 || d->nidx[i] >= d->nvn)
-                return fail(ctx, GRB_ERR_INVALID, "normal index out of range (the reference panics: renderer.go:328-330)");
-    }
+    if (d->nvn > 0 && (!d->vnormals || !d->nidx))
+        return fail(ctx, GRB_ERR_INVALID, "mesh with vertex normals needs normal indices");
     if (int32_t r = set_device(ctx)) return r;
     MeshHost m;
     m.live = true;
@@ -644,12 +655,22 @@ int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_i
     float4 *f4;
     int32_t *i32;
     float2 *f2;
+    uint32_t *scratch = nullptr;   // [0..6] bbox keys + NaN bits, [7] index-check flags
+    const uint32_t scratchInit[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+    uint32_t scratchHost[8];
+    MeshPrepArgs pa{};
+    cudaStream_t s = ctx->stream;
     if ((r = upload(ctx, reinterpret_cast<const float4 *>(d->vertices), d->nv, &f4, m.allocs))) goto bad;
     m.dev.verts = f4;
     if ((r = upload(ctx, reinterpret_cast<const float4 *>(d->vnormals), d->nvn, &f4, m.allocs))) goto bad;
     m.dev.vnormals = f4;
-    if ((r = upload(ctx, reinterpret_cast<const float4 *>(d->fnormals), d->nf, &f4, m.allocs))) goto bad;
+    if (derive) {
+        if ((r = dev_alloc(ctx, (size_t)d->nf, &f4, m.allocs))) goto bad;
+    } else {
+        if ((r = upload(ctx, reinterpret_cast<const float4 *>(d->fnormals), d->nf, &f4, m.allocs))) goto bad;
+    }
     m.dev.fnormals = f4;
+    pa.fnormalsOut = derive ? f4 : nullptr;
     if ((r = upload(ctx, d->vidx, (size_t)d->nf * 3, &i32, m.allocs))) goto bad;
     m.dev.vidx = i32;
     if ((r = upload(ctx, d->nvn > 0 ? d->nidx : nullptr, (size_t)d->nf * 3, &i32, m.allocs))) goto bad;
@@ -658,21 +679,65 @@ int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_i
     m.dev.uvs = f2;
     if ((r = upload(ctx, d->tex, d->nf, &i32, m.allocs))) goto bad;
     m.dev.tex = i32;
-    {   // face-corner expansion (gr_types.cuh): corner k of face f at cv[k][f]
-        std::vector<float4> corner(d->nf);
-        const float4 *hv = reinterpret_cast<const float4 *>(d->vertices);
-        const float4 *hn = reinterpret_cast<const float4 *>(d->vnormals);
-        for (int k = 0; k < 3; k++) {
-            for (int32_t f = 0; f < d->nf; f++) corner[f] = hv[d->vidx[3 * f + k]];
-            if ((r = upload(ctx, corner.data(), d->nf, &f4, m.allocs))) goto bad;
-            m.dev.cv[k] = f4;
-            m.dev.cn[k] = nullptr;
-            if (d->nvn > 0) {
-                for (int32_t f = 0; f < d->nf; f++) corner[f] = hn[d->nidx[3 * f + k]];
-                if ((r = upload(ctx, corner.data(), d->nf, &f4, m.allocs))) goto bad;
-                m.dev.cn[k] = f4;
-            }
+    for (int k = 0; k < 3; k++) {   // face-corner expansion (gr_types.cuh): corner k of face f at cv[k][f]
+        if ((r = dev_alloc(ctx, (size_t)d->nf, &f4, m.allocs))) goto bad;
+        m.dev.cv[k] = f4;
+        pa.cv[k] = f4;
+        m.dev.cn[k] = nullptr;
+        if (d->nvn > 0) {
+            if ((r = dev_alloc(ctx, (size_t)d->nf, &f4, m.allocs))) goto bad;
+            m.dev.cn[k] = f4;
         }
+        pa.cn[k] = f4;
+    }
+    if ((r = dev_alloc(ctx, (size_t)8, &scratch, m.allocs))) goto bad;
+    pa.verts = m.dev.verts; pa.vnormals = m.dev.vnormals; pa.vidx = m.dev.vidx; pa.nidx = m.dev.nidx;
+    pa.nv = d->nv; pa.nvn = d->nvn; pa.nf = d->nf;
+    pa.error = reinterpret_cast<int *>(scratch + 7);
+    {
+        cudaError_t e = cudaMemcpyAsync(scratch, scratchInit, sizeof(scratchInit), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            launch_mesh_prepare(pa, s);
+            if (derive) launch_bbox(m.dev.verts, d->nv, scratch, s);
+            ctx->totalLaunches += (d->nf > 0 ? 1 : 0) + (derive ? 1 : 0);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(scratchHost, scratch, sizeof(scratchHost), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            r = fail(ctx, GRB_ERR_CUDA, std::string("mesh preparation: ") + cudaGetErrorString(e));
+            goto bad;
+        }
+    }
+    // the reference would panic on an out-of-range index (renderer.go:318-320, 328-330)
+    if (scratchHost[7] & 1u) { r = fail(ctx, GRB_ERR_INVALID, "vertex index out of range"); goto bad; }
+    if (scratchHost[7] & 2u) {
+        r = fail(ctx, GRB_ERR_INVALID, "normal index out of range (the reference panics: renderer.go:328-330)");
+        goto bad;
+    }
+    if (derive) {
+        // boundingBox (mesh.go:28-51): corners in min/max order x, then y, then z
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; k++) {
+            auto from_key = [](uint32_t key) {
+                const uint32_t b = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+                float f;
+                std::memcpy(&f, &b, 4);
+                return f;
+            };
+            lo[k] = from_key(scratchHost[k]);
+            hi[k] = from_key(scratchHost[3 + k]);
+            if (scratchHost[6] & (1u << k)) lo[k] = hi[k] = std::numeric_limits<float>::quiet_NaN();  // Go's min/max propagate NaN
+        }
+        int c = 0;
+        for (int ix = 0; ix < 2; ix++)
+            for (int iy = 0; iy < 2; iy++)
+                for (int iz = 0; iz < 2; iz++, c++) {
+                    m.bbox[4 * c] = ix ? hi[0] : lo[0];
+                    m.bbox[4 * c + 1] = iy ? hi[1] : lo[1];
+                    m.bbox[4 * c + 2] = iz ? hi[2] : lo[2];
+                    m.bbox[4 * c + 3] = 1.0f;
+                }
     }
     ctx->meshes.push_back(std::move(m));
     ctx->meshesDirty = true;
@@ -682,6 +747,31 @@ int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_i
 bad:
     for (void *p : m.allocs) cudaFree(p);
     return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_id) {
+    return mesh_upload_impl(ctx, d, false, out_id);
+}
+
+int32_t grb_mesh_new(grb_context *ctx, const grb_mesh_desc *d, int32_t *out_id) {
+    return mesh_upload_impl(ctx, d, true, out_id);
+}
+
+int32_t grb_mesh_read_derived(grb_context *ctx, int32_t id, float *fnormals, float bbox[32]) {
+    if (!ctx || id < 0 || id >= (int32_t)ctx->meshes.size() || !ctx->meshes[id].live)
+        return fail(ctx, GRB_ERR_INVALID, "bad mesh id");
+    if (int32_t r = set_device(ctx)) return r;
+    const MeshHost &m = ctx->meshes[id];
+    if (bbox) std::memcpy(bbox, m.bbox, sizeof(m.bbox));
+    if (fnormals && m.dev.nf > 0) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaMemcpy(fnormals, m.dev.fnormals, (size_t)m.dev.nf * sizeof(float4), cudaMemcpyDeviceToHost));
+    }
+    return GRB_OK;
 }
 
 int32_t grb_mesh_free(grb_context *ctx, int32_t id) {

@@ -50,6 +50,16 @@ struct MeshDev {
     int32_t nv, nvn, nf, pad;
 };
 
+// upload-time preparation of one mesh (mesh.cu)
+struct MeshPrepArgs {
+    const float4 *verts, *vnormals;
+    const int32_t *vidx, *nidx;
+    int32_t nv, nvn, nf;
+    float4 *cv[3], *cn[3];
+    float4 *fnormalsOut;     // null: face normals were supplied by the caller
+    int *error;              // bit 0: vertex index out of range, bit 1: normal index out of range
+};
+
 struct TexDev {
     const uchar4 *pixels;
     int32_t type, width, height;

@@ -13,6 +13,9 @@ void launch_transform(const DrawArgs &a, int nframes, cudaStream_t s);
 void launch_setup(const DrawArgs &a, int nframes, bool anyPlain, bool anyClip, cudaStream_t s);
 // K3: per-tile coverage + z resolve in shared memory, shade, coalesced write-back.
 void launch_raster(const DrawArgs &a, int nframes, cudaStream_t s);
+// Upload time: index check + face-corner expansion (+ NewMesh's face normals), boundingBox keys.
+void launch_mesh_prepare(const MeshPrepArgs &p, cudaStream_t s);
+void launch_bbox(const float4 *verts, int nv, uint32_t *out7, cudaStream_t s);
 // matrixMultiplyVec4Batch over a device array.
 void launch_matvec_batch(const float m[16], float4 *vecs, long long n, cudaStream_t s);
 

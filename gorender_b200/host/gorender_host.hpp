@@ -545,6 +545,24 @@ public:
     int32_t meshID(const MeshPtr &m) {  // flattens Faces (mesh.go:12-17) once
         auto it = meshes_.find(m.get());
         if (it != meshes_.end()) return it->second;
+        return uploadMesh(m, false);
+    }
+    // NewMesh (mesh.go:53-69) with the face normals and the bounding box computed by the GPU while
+    // the mesh is uploaded (grb_mesh_new), then copied back into the Mesh fields.
+    MeshPtr NewMesh(std::vector<Vec4> vertices, std::vector<Vec4> vertexNormals, std::vector<Face> faces) {
+        auto m = std::make_shared<Mesh>();
+        m->Faces = std::move(faces);
+        m->Vertices = std::move(vertices);
+        m->VertexNormals = std::move(vertexNormals);
+        m->FaceNormals.resize(m->Faces.size());
+        const int32_t id = uploadMesh(m, true);
+        check(grb_mesh_read_derived(ctx_, id, m->FaceNormals.empty() ? nullptr : &m->FaceNormals[0].X, &m->BoundingBox[0].X),
+              "grb_mesh_read_derived");
+        return m;
+    }
+
+private:
+    int32_t uploadMesh(const MeshPtr &m, bool derive) {
         const size_t nf = m->Faces.size();
         std::vector<int32_t> vidx(3 * nf), nidx(3 * nf), tex(nf);
         std::vector<float> uvs(6 * nf);
@@ -569,12 +587,12 @@ public:
         d.tex = nf ? tex.data() : nullptr;
         std::memcpy(d.bbox, m->BoundingBox, sizeof(d.bbox));
         int32_t id = -1;
-        check(grb_mesh_upload(ctx_, &d, &id), "grb_mesh_upload");
+        if (derive) check(grb_mesh_new(ctx_, &d, &id), "grb_mesh_new");
+        else check(grb_mesh_upload(ctx_, &d, &id), "grb_mesh_upload");
         keepM_.push_back(m);
         return meshes_[m.get()] = id;
     }
 
-private:
     grb_context *ctx_ = nullptr;
     std::map<const Texture *, int32_t> textures_;
     std::map<const Mesh *, int32_t> meshes_;

@@ -91,21 +91,27 @@ def faceNormals(vertices: np.ndarray, vidx: np.ndarray) -> np.ndarray:
 class Mesh:
     """mesh.go:19-26."""
 
-    def __init__(self, Vertices, VertexNormals, Faces: FaceArray, Name: str = ""):
+    def __init__(self, Vertices, VertexNormals, Faces: FaceArray, Name: str = "", device=None):
         self.Name = Name
         self.Vertices = np.ascontiguousarray(Vertices, dtype=np.float32).reshape(-1, 4)
         self.VertexNormals = np.ascontiguousarray(
             VertexNormals if VertexNormals is not None else np.zeros((0, 4)), dtype=np.float32).reshape(-1, 4)
         self.Faces = Faces
-        if len(Faces) and (Faces.VertexIndices.min() < 0 or Faces.VertexIndices.max() >= len(self.Vertices)):
-            raise IndexError("face vertex index out of range")  # the reference panics (mesh.go:56-58)
-        self.FaceNormals = faceNormals(self.Vertices, Faces.VertexIndices)
-        self.BoundingBox = boundingBox(self.Vertices)
+        if device is None:
+            if len(Faces) and (Faces.VertexIndices.min() < 0 or Faces.VertexIndices.max() >= len(self.Vertices)):
+                raise IndexError("face vertex index out of range")  # the reference panics (mesh.go:56-58)
+            self.FaceNormals = faceNormals(self.Vertices, Faces.VertexIndices)
+            self.BoundingBox = boundingBox(self.Vertices)
+        else:
+            # NewMesh on the device (grb_mesh_new): the upload computes both and fills these in
+            self.FaceNormals = self.BoundingBox = None
+            device.mesh_id(self)
 
 
-def NewMesh(vertices, vertexNormals, faces: FaceArray) -> Mesh:
-    """mesh.go:53-69."""
-    return Mesh(vertices, vertexNormals, faces)
+def NewMesh(vertices, vertexNormals, faces: FaceArray, device=None) -> Mesh:
+    """mesh.go:53-69.  With `device`, the face normals and the bounding box are computed by the GPU
+    while the mesh is uploaded instead of by numpy on the host."""
+    return Mesh(vertices, vertexNormals, faces, device=device)
 
 
 class Object:

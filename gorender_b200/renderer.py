@@ -105,11 +105,14 @@ class Device:
         ent = self._meshes.get(id(m))
         if ent is not None and ent[2] == tex_ids and ent[3] is F.TextureIndex:
             return ent[0]
+        # a mesh built with NewMesh(..., device=dev) has no derived arrays yet: NewMesh's face
+        # normals and bounding box (mesh.go:53-69) are computed on the device and copied back
+        derive = m.FaceNormals is None
         d = _cabi.grb_mesh_desc()
         nf = len(F)
         verts = np.ascontiguousarray(m.Vertices, dtype=np.float32)
         vns = np.ascontiguousarray(m.VertexNormals, dtype=np.float32)
-        fns = np.ascontiguousarray(m.FaceNormals, dtype=np.float32)
+        fns = None if derive else np.ascontiguousarray(m.FaceNormals, dtype=np.float32)
         vidx = np.ascontiguousarray(F.VertexIndices, dtype=np.int32)
         nidx = np.ascontiguousarray(F.NormalIndices, dtype=np.int32)
         uvs = np.ascontiguousarray(F.UVs, dtype=np.float32)
@@ -118,15 +121,22 @@ class Device:
         d.nv, d.nvn, d.nf = len(verts), len(vns), nf
         d.vertices = _cabi.ptr(verts, C.c_float)
         d.vnormals = _cabi.ptr(vns, C.c_float) if len(vns) else None
-        d.fnormals = _cabi.ptr(fns, C.c_float) if nf else None
+        d.fnormals = _cabi.ptr(fns, C.c_float) if (nf and not derive) else None
         d.vidx = _cabi.ptr(vidx, C.c_int32) if nf else None
         d.nidx = _cabi.ptr(nidx, C.c_int32) if (nf and len(vns)) else None
         d.uvs = _cabi.ptr(uvs, C.c_float) if nf else None
         d.tex = _cabi.ptr(tex, C.c_int32) if nf else None
-        bbox = np.ascontiguousarray(m.BoundingBox, dtype=np.float32).reshape(32)
-        d.bbox = (C.c_float * 32)(*bbox.tolist())
         out = C.c_int32(-1)
-        self.check(self.lib.grb_mesh_upload(self.h, C.byref(d), C.byref(out)))
+        if derive:
+            self.check(self.lib.grb_mesh_new(self.h, C.byref(d), C.byref(out)))
+            fn = np.empty((nf, 4), np.float32)
+            bb = np.empty((8, 4), np.float32)
+            self.check(self.lib.grb_mesh_read_derived(self.h, out.value, _cabi.ptr(fn) if nf else None, _cabi.ptr(bb)))
+            m.FaceNormals, m.BoundingBox = fn, bb
+        else:
+            bbox = np.ascontiguousarray(m.BoundingBox, dtype=np.float32).reshape(32)
+            d.bbox = (C.c_float * 32)(*bbox.tolist())
+            self.check(self.lib.grb_mesh_upload(self.h, C.byref(d), C.byref(out)))
         if ent is not None:
             self.check(self.lib.grb_mesh_free(self.h, ent[0]))
         self._meshes[id(m)] = (out.value, m, tex_ids, F.TextureIndex)

@@ -170,6 +170,12 @@ int32_t grb_texture_upload(grb_context *ctx, int32_t type, int32_t width, int32_
 /* Texture.SetScale (texture.go:65-67). */
 int32_t grb_texture_set_scale(grb_context *ctx, int32_t id, float scale);
 int32_t grb_mesh_upload(grb_context *ctx, const grb_mesh_desc *desc, int32_t *out_id);
+/* NewMesh (mesh.go:53-69) on the device: like grb_mesh_upload, but Mesh.FaceNormals (mesh.go:54-60)
+ * and Mesh.BoundingBox (mesh.go:28-51) are computed on the GPU from the uploaded vertices and
+ * indices; desc->fnormals and desc->bbox are ignored.  grb_mesh_read_derived copies them back for
+ * the caller's Mesh fields (fnormals: nf*4 floats; bbox: 8 corners * xyzw); either may be NULL. */
+int32_t grb_mesh_new(grb_context *ctx, const grb_mesh_desc *desc, int32_t *out_id);
+int32_t grb_mesh_read_derived(grb_context *ctx, int32_t id, float *fnormals, float bbox[32]);
 int32_t grb_mesh_free(grb_context *ctx, int32_t id);
 
 /* ---- framebuffer: NewFrameBuffer (rasterizer.go:15-23) ------------------

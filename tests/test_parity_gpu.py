@@ -300,6 +300,57 @@ def test_full_size_c5_pose_batch(device, oracle):
     assert np.array_equal(px[0], sample[0][0]) and np.array_equal(z[0].view(np.uint32), sample[0][1].view(np.uint32))
 
 
+def _bits_equal_nan_aware(got, want):
+    nan = np.isnan(want)
+    return np.array_equal(np.isnan(got), nan) and np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan])
+
+
+@pytest.mark.parametrize("which", ["suzanne", "cube", "sphere30_vn", "soup"])
+def test_new_mesh_on_device(which, device, oracle):
+    """NewMesh (mesh.go:53-69) on the device: face normals and bounding box bit for bit against the
+    oracle's restatement and the host (numpy) mirror; the mesh then renders exactly like a host-built one."""
+    if which == "suzanne":
+        host = workloads.suzanne()
+    elif which == "cube":
+        host = workloads.cube()
+    elif which == "sphere30_vn":
+        host = geometry.geodesic_sphere(30, True, workloads.checker_texture(32))
+    else:
+        rng = np.random.default_rng(7)
+        nv = 5000
+        verts = np.ones((nv, 4), np.float32)
+        verts[:, :3] = (rng.normal(0, 2, (nv, 3)) * rng.choice([1e-3, 1.0, 1e3], (nv, 1))).astype(np.float32)
+        verts[17, :3] = (-0.0, 0.0, -0.0)
+        vidx = rng.integers(0, nv, (20000, 3)).astype(np.int32)
+        vidx[::5, 2] = vidx[::5, 1]                      # degenerate faces: 0/0 -> NaN normals
+        host = g.NewMesh(verts, None, g.FaceArray(vidx))
+    F = host.Faces
+    dev_mesh = g.NewMesh(host.Vertices, host.VertexNormals if len(host.VertexNormals) else None,
+                         g.FaceArray(F.VertexIndices, F.NormalIndices, F.UVs, F.TextureIndex, F.Textures), device=device)
+    want_fn = oracle.face_normals(host.Vertices, F.VertexIndices)
+    want_bb = oracle.bounding_box(host.Vertices)
+    assert dev_mesh.FaceNormals.shape == want_fn.shape
+    assert _bits_equal_nan_aware(dev_mesh.FaceNormals, want_fn)
+    assert _bits_equal_nan_aware(host.FaceNormals, want_fn)
+    assert np.array_equal(dev_mesh.BoundingBox.view(np.uint32), want_bb.reshape(8, 4).view(np.uint32))
+    if which != "soup":
+        cam = geometry.default_camera()
+        fb = g.FrameBuffer(640, 360, 2, device)
+        r = g.Renderer(fb)
+        px, z, tpf = r.DrawBatch([g.NewObject(host)], [cam])
+        px2, z2, tpf2 = r.DrawBatch([g.NewObject(dev_mesh)], [cam])
+        assert int(tpf[0]) == int(tpf2[0]) and np.array_equal(px[0], px2[0])
+        assert np.array_equal(z[0].view(np.uint32), z2[0].view(np.uint32))
+
+
+def test_new_mesh_on_device_rejects_bad_indices(device):
+    verts = np.ones((4, 4), np.float32)
+    with pytest.raises(g.renderer._cabi.GorenderError):
+        g.NewMesh(verts, None, g.FaceArray(np.array([[0, 1, 4]], np.int32)), device=device)
+    with pytest.raises(g.renderer._cabi.GorenderError):
+        g.NewMesh(verts, None, g.FaceArray(np.array([[0, -1, 2]], np.int32)), device=device)
+
+
 def test_errors_are_loud(device):
     fb = g.FrameBuffer(64, 64, 1, device)
     r = g.Renderer(fb)
