@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgorender_b200.so")
+# GORENDER_B200_LIB: another build of the same library (kernel tuning variants, scripts/tune.sh)
+LIB_PATH = os.environ.get("GORENDER_B200_LIB") or os.path.join(_HERE, "lib", "libgorender_b200.so")
 
 GRB_OK = 0
 GRB_OPT_FRUSTUM_CLIPPING = 1 << 0

@@ -11,10 +11,12 @@
 // (rasterizer.go:156): later triangles win ties, so the surviving fragment of
 // a pixel is the lexicographic maximum of (zRec, submission order) — which is
 // exactly max(key), in any processing order.  Phase A resolves coverage and
-// depth for all triangles of the tile in parallel, each warp working through
-// its share of the tile's descriptor list without block barriers (small
-// triangles: warp-wide coarse / fine stages; large ones: the warp sweeps the
-// tile rows; always a shared-memory atomic max on the key).  Phase B shades only the
+// depth for all triangles of the tile in parallel: the tile's descriptors are
+// scattered into a shared list of record slots and the warps take 32 of them
+// at a time (tiny triangles: each lane tests its own 4x4 block, the covered
+// pixels of the whole warp then run the divide-heavy fine stage densely;
+// medium ones: bbox rows dealt to the lanes; large ones: a block-wide pass with
+// thread-owned pixels; otherwise a shared-memory atomic max on the key).  Phase B shades only the
 // winning fragment of each pixel (perspective-correct UV, Gouraud intensity,
 // nearest texel through the read-only path), generates the cleared
 // background and dot grid for uncovered pixels, and writes colour and depth
@@ -30,9 +32,16 @@
 namespace gr {
 
 constexpr int kRasterThreads = 256;
-constexpr int kRasterBlocksPerSM = 6;  // resident blocks per SM the register budget is held to
+#ifndef GRB_SLOTWIN
+#define GRB_SLOTWIN 2048
+#endif
+#ifndef GRB_RASTER_BLOCKS
+#define GRB_RASTER_BLOCKS 5   // 48 registers: measured faster than 6 blocks at 40 registers with spills
+#endif
+constexpr int kRasterBlocksPerSM = GRB_RASTER_BLOCKS;  // resident blocks per SM the register budget is held to
 constexpr int kSmallArea = 32;  // bbox∩tile pixels up to which a triangle takes the warp-level coarse/fine path
 constexpr int kSmallWidth = 8;  // ... and the widest bbox row that path walks
+constexpr int kTinyEdge = 4;    // bbox∩tile of at most kTinyEdge x kTinyEdge pixels: tested by its own lane, fully unrolled
 constexpr unsigned long long kBackgroundKey = 0x407FFFFFull << 32;  // orderable(-1.0f) (rasterizer.go:37)
 
 __device__ __forceinline__ uint32_t orderable(float z) {
@@ -113,14 +122,19 @@ __device__ __forceinline__ uchar4 sample_texture(const TexDev &t, float u, float
 //
 // A warp takes 32 list entries at a time.  Each lane sets up its triangle (edge functions, the
 // bbox clipped to the tile) into a per-warp shared-memory table, struct-of-arrays so that lanes
-// reading different triangles hit different banks.  The bbox ROWS of all 32 triangles are then
-// flattened into one work list (warp prefix sum of the row counts); a lane takes a row, evaluates
-// the three edge functions once at its left end and steps along its few pixels — coarse stage,
-// integer adds only.  Covered (triangle, pixel) pairs are pushed into a
-// per-warp ring; whenever 32 are available the fine stage runs with every lane busy: 5 IEEE
-// divides for zRec (rasterizer.go:149-153) and a shared-memory atomic max on the pixel's key.
-// One lane per triangle would execute the divide sequence at the occupancy of the rare covered
-// pixels; this way the expensive part runs dense.
+// reading different triangles hit different banks.  Coarse stage, integer adds only: a triangle
+// whose clipped bbox fits 4 x 4 pixels (nearly all of a dense mesh) is tested by its own lane, all
+// 16 pixels unrolled into a bit mask; for wider ones (up to 8 x 4) the bbox ROWS of the warp's
+// triangles are flattened into one work list (warp prefix sum of the row counts) and a lane takes
+// a row.  Covered (triangle, pixel) pairs are pushed into a per-warp ring; whenever 32 are
+// available the fine stage runs with every lane busy: 5 IEEE divides for zRec
+// (rasterizer.go:149-153) and a shared-memory atomic max on the pixel's key.  One lane per
+// triangle would execute the divide sequence at the occupancy of the rare covered pixels; this
+// way the expensive part runs dense.
+//
+// Shared memory is kept small on purpose: the record gathers of this phase live on L1, and every
+// 32 KB of carveout the blocks do not need costs measurable time (a double-buffered table that
+// avoided the sparse drain after each batch was slower for exactly that reason).
 
 struct WarpTris {            // one per warp, 32 triangles
     int a01[32], b01[32], c01[32];
@@ -131,8 +145,9 @@ struct WarpTris {            // one per warp, 32 triangles
     uint32_t box[32];        // local x0 | local y0 << 5 | bw << 10
 };
 constexpr int kFragRing = 64;
-constexpr int kLargeQueue = 1024;  // large triangles a block queues per round before falling back to warp sweeps
+constexpr int kLargeQueue = 1024;  // large triangles a block queues per window before falling back to warp sweeps
 constexpr int kDescRound = 256;    // descriptors expanded per round (one per thread)
+constexpr int kSlotWin = GRB_SLOTWIN;      // record slots of a round held in shared memory at a time
 
 // fine stage for `count` (<= 32) queued fragments starting at ring position `head`
 __device__ __forceinline__ void fine_stage(const WarpTris &wt, const uint32_t *ring, uint32_t head, int count, int lane,
@@ -265,8 +280,8 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
                                               int tileX1, int tileY1, unsigned long long *keys, uint32_t *largeQ,
                                               int *largeCount) {
     const unsigned ltMask = (1u << lane) - 1u;
-    int rows = 0;   // bbox rows of this lane's triangle inside the tile (0: nothing for the small path)
-    bool large = false;
+    int rows = 0;   // bbox rows of this lane's triangle inside the tile (0: nothing for the small paths)
+    bool large = false, tiny = false;
     if (have) {
         const TriRec r = load_rec(rec + slot);
         const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
@@ -282,20 +297,73 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
                 wt.slot[lane] = slot;
                 wt.box[lane] = (uint32_t)(x0 - tileX) | ((uint32_t)(y0 - tileY) << 5) | ((uint32_t)bw << 10);
                 rows = bh;
+                tiny = bw <= kTinyEdge && bh <= kTinyEdge;
             } else {
                 large = true;
             }
         }
     }
-    // ---- small triangles: flatten the bbox ROWS of the 32 triangles into one list; a lane takes a
-    //      row, sets the three edge functions up once and walks its (at most kSmallWidth) pixels
-    int incl = rows;
+    // ---- tiny triangles (the bulk of a dense mesh): every lane tests the few pixels of its own
+    //      triangle's bbox with integer adds and keeps the covered ones as a bit mask (bit = 8 * row
+    //      + column); the fragments of the 32 masks then go into the ring
+    uint32_t cover = 0u;
+    if (tiny) {
+        const uint32_t box = wt.box[lane];
+        const int bw = (int)(box >> 10), lx0 = (int)(box & 31u), ly0 = (int)((box >> 5) & 31u);
+        const int x = tileX + lx0, y = tileY + ly0;
+        const int a01 = wt.a01[lane], a12 = wt.a12[lane], a20 = wt.a20[lane];
+        const int b01 = wt.b01[lane], b12 = wt.b12[lane], b20 = wt.b20[lane];
+        int r01 = a01 * x + b01 * y + wt.c01[lane];
+        int r12 = a12 * x + b12 * y + wt.c12[lane];
+        int r20 = a20 * x + b20 * y + wt.c20[lane];
+        // all 16 pixels of the 4 x 4 block at the bbox origin, no loop control; the ones outside the
+        // bbox (or the tile) are masked off afterwards
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
+        for (int j = 0; j < 4; j++) {
+            int f01 = r01, f12 = r12, f20 = r20;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                cover |= ((uint32_t)(f01 & f12 & f20) >> (31 - (8 * j + k))) & (1u << (8 * j + k));
+                f01 += a01; f12 += a12; f20 += a20;
+            }
+            r01 += b01; r12 += b12; r20 += b20;
+        }
+        const uint32_t rowMask = ((1u << bw) - 1u) * 0x01010101u;
+        cover &= rowMask & (0xffffffffu >> (32 - 8 * rows));   // rows in 1..4
+        rows = 0;  // not for the row path below
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    {
+        const uint32_t box = wt.box[lane];
+        const uint32_t origin = ((uint32_t)lane << 10) | (box & 1023u);  // t | ly0 << 5 | lx0
+        unsigned pending = __ballot_sync(0xffffffffu, cover != 0);
+        while (pending) {
+            const bool emit = cover != 0;
+            if (emit) {
+                const int bit = __ffs((int)cover) - 1;
+                cover &= cover - 1u;
+                ring[(qTail + __popc(pending & ltMask)) & (kFragRing - 1)] =
+                    origin + (uint32_t)(bit & 7) + ((uint32_t)(bit >> 3) << 5);
+            }
+            qTail += __popc(pending);
+            __syncwarp();
+            if (qTail - qHead >= 32) {
+                fine_stage(wt, ring, qHead, 32, lane, tileX, tileY, keys);
+                qHead += 32;
+            }
+            pending = __ballot_sync(0xffffffffu, cover != 0);
+        }
+    }
+    // ---- medium triangles: flatten the bbox ROWS of the warp's triangles into one list; a lane takes a
+    //      row, sets the three edge functions up once and walks its (at most kSmallWidth) pixels
+    int incl = rows, total = 0;
+    if (__any_sync(0xffffffffu, rows != 0)) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+    }
     const int excl = incl - rows;
     __syncwarp();
     for (int item0 = 0; item0 < total; item0 += 32) {
@@ -428,8 +496,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     __shared__ unsigned long long keys[kTilePix];
     __shared__ WarpTris tris[kRasterThreads / 32];
     __shared__ uint32_t fragRing[kRasterThreads / 32][kFragRing];
-    __shared__ TileDesc dList[kDescRound];
-    __shared__ uint32_t dStart[kDescRound + 1];
+    __shared__ uint32_t slotList[kSlotWin];
     __shared__ uint32_t warpSums[kRasterThreads / 32];
     __shared__ uint32_t largeQ[kLargeQueue];
     __shared__ int largeCount;
@@ -541,8 +608,8 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                 __syncthreads();
                 continue;
             }
-            // -- block-wide exclusive scan of the triangle counts: entry e belongs to the descriptor
-            //    with dStart[i] <= e < dStart[i+1], so entries can be dealt to the warps evenly
+            // -- block-wide exclusive scan of the triangle counts: the slots of this thread's
+            //    descriptor are entries [first, first + cnt) of the round
             const uint32_t cnt = __popc(d.mask);
             uint32_t incl = cnt;
 #pragma unroll
@@ -551,7 +618,6 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                 if (lane >= s_) incl += v;
             }
             if (lane == 31) warpSums[warp] = incl;
-            if (tid == 0) largeCount = 0;
             __syncthreads();
             uint32_t wbase = 0, total = 0;
 #pragma unroll
@@ -560,33 +626,44 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                 if (w < warp) wbase += v;
                 total += v;
             }
-            dList[tid] = d;
-            dStart[tid] = wbase + incl - cnt;
-            if (tid == 0) dStart[kDescRound] = total;
-            __syncthreads();
-            // -- batches of 32 entries, round-robin over the warps
-            const uint32_t nBatches = (total + 31) / 32;
-            for (uint32_t b = warp; b < nBatches; b += kWarps) {
-                const uint32_t e = b * 32 + lane;
-                const bool have = e < total;
-                uint32_t slot = 0;
-                if (have) {
-                    int lo = 0;  // largest i with dStart[i] <= e
-#pragma unroll
-                    for (int step = kDescRound / 2; step >= 1; step >>= 1)
-                        if (dStart[lo + step] <= e) lo += step;
-                    const TileDesc dd = dList[lo];
-                    slot = dd.base + (uint32_t)__fns(dd.mask, 0, (int)(e - dStart[lo]) + 1);
-                }
-                process_batch(have, slot, rec, wt, ring, qHead, qTail, lane, tileX, tileY, tileX1, tileY1, keys, largeQ,
-                              &largeCount);
-            }
-            __syncthreads();
-            // -- large triangles found in this round
-            const int nq = min(largeCount, kLargeQueue);
-            if (nq) {
-                coop_pass(largeQ, nq, rec, gx, gy, px, py, keys);
+            const uint32_t first = wbase + incl - cnt;
+            if (total == 0) {  // (an overflow round without entries for this tile) warpSums is rewritten next round
                 __syncthreads();
+                continue;
+            }
+            // -- windows of kSlotWin entries: every thread scatters its descriptor's record slots
+            //    into the shared list (one store per triangle, no searching), then the warps take
+            //    32 consecutive entries at a time
+            for (uint32_t win0 = 0; win0 < total; win0 += kSlotWin) {
+                if (tid == 0) largeCount = 0;
+                if (first < win0 + kSlotWin && first + cnt > win0) {
+                    uint32_t m = d.mask, pos = first - win0;  // wraps below the window: fails the range test
+                    while (m) {
+                        const uint32_t b = (uint32_t)__ffs(m) - 1u;
+                        m &= m - 1u;
+                        if (pos < (uint32_t)kSlotWin) {
+                            slotList[pos] = d.base + b;
+                        }
+                        pos++;
+                    }
+                }
+                __syncthreads();
+                const uint32_t nWin = min(total - win0, (uint32_t)kSlotWin);
+                const uint32_t nBatches = (nWin + 31) / 32;
+                for (uint32_t b = warp; b < nBatches; b += kWarps) {
+                    const uint32_t e = b * 32 + lane;
+                    const bool have = e < nWin;
+                    const uint32_t slot = have ? slotList[e] : 0u;
+                    process_batch(have, slot, rec, wt, ring, qHead, qTail, lane, tileX, tileY, tileX1, tileY1, keys, largeQ,
+                                  &largeCount);
+                }
+                __syncthreads();
+                // -- large triangles found in this window
+                const int nq = min(largeCount, kLargeQueue);
+                if (nq) {
+                    coop_pass(largeQ, nq, rec, gx, gy, px, py, keys);
+                    __syncthreads();
+                }
             }
         }
     }
@@ -656,6 +733,17 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
 void launch_raster(const DrawArgs &a, int nframes, cudaStream_t s) {
     const int rows = a.tileRowEnd - a.tileRowBegin;
     if (rows <= 0 || a.ntx <= 0) return;
+    // the record gathers of phase A live on L1: a larger shared-memory carveout than the blocks need costs time
+#ifndef GRB_CARVEOUT
+#define GRB_CARVEOUT -1   // percent of the SM's L1/shared storage asked for as shared memory; -1: the driver's choice
+#endif
+    static const bool carveout = [] {
+        if (GRB_CARVEOUT < 0) return false;
+        cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, GRB_CARVEOUT);
+        cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, GRB_CARVEOUT);
+        return true;
+    }();
+    (void)carveout;
     if (a.options & kOptPostPass)
         raster_kernel<true><<<dim3(a.ntx, rows, nframes), kRasterThreads, 0, s>>>(a);
     else

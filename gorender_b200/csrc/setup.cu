@@ -28,6 +28,10 @@
 #include "gr_types.cuh"
 #include "kernels.h"
 
+#ifndef GRB_SETUP_BLOCKS
+#define GRB_SETUP_BLOCKS 5   // resident 256-thread blocks per SM the register budget is held to
+#endif
+
 namespace gr {
 
 // ---------------------------------------------------------------- K1
@@ -361,7 +365,7 @@ struct __align__(16) StagedFace {
 // OVL: the instantiation that also draws the ShowEdges / ShowVertices overlays (as event keys into
 // a.ovl); the frame path proper is the OVL = false one.
 template <bool CLIP, bool OVL>
-__global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : 5) setup_kernel(const __grid_constant__ DrawArgs a) {
+__global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_kernel(const __grid_constant__ DrawArgs a) {
     const int frame = blockIdx.y;
     const int fb = blockIdx.x;
     const int o = a.fblkObj[fb];
