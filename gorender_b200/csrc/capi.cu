@@ -417,12 +417,34 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.options = prm->options;
     a.zNear = prm->z_near;
     a.zFar = prm->z_far;
+    a.screenNoZ = prm->screen[2] == 0.0f && prm->screen[6] == 0.0f;
     if (prm->ref_tiles == 1) {
-        a.ref = {1, 1, fb->width, fb->height};
+        a.ref.ntx = a.ref.nty = 1;
+        a.ref.tw = fb->width;
+        a.ref.th = fb->height;
     } else {
         // calculateTileBoundaries (renderer.go:56-59) for numTiles = 16
         const int n = 16, rtx = 4, rty = (n + rtx - 1) / rtx;
-        a.ref = {rtx, rty, (fb->width + rtx - 1) / rtx, (fb->height + rty - 1) / rty};
+        a.ref.ntx = rtx;
+        a.ref.nty = rty;
+        a.ref.tw = (fb->width + rtx - 1) / rtx;
+        a.ref.th = (fb->height + rty - 1) / rty;
+    }
+    {   // renderer.go:62-73 per column and per row (numTiles == 1: the whole frame, :51-53)
+        const float Wf = (float)fb->width, Hf = (float)fb->height, nan = std::numeric_limits<float>::quiet_NaN();
+        for (int c = 0; c < 4; c++) {
+            a.ref.sx[c] = a.ref.ex[c] = a.ref.sy[c] = a.ref.ey[c] = nan;
+            if (c < a.ref.ntx) {
+                a.ref.sx[c] = (float)(c * a.ref.tw);
+                a.ref.ex[c] = a.ref.sx[c] + (float)a.ref.tw;
+                if (a.ref.ntx == 1 || a.ref.ex[c] > Wf) a.ref.ex[c] = Wf;
+            }
+            if (c < a.ref.nty) {
+                a.ref.sy[c] = (float)(c * a.ref.th);
+                a.ref.ey[c] = a.ref.sy[c] + (float)a.ref.th;
+                if (a.ref.nty == 1 || a.ref.ey[c] > Hf) a.ref.ey[c] = Hf;
+            }
+        }
     }
 
     const bool anyVisible = anyPlain || anyClip;

@@ -133,8 +133,10 @@ constexpr uint32_t kOptOverlayKeys = GRB_OPT_SHOW_EDGES | GRB_OPT_SHOW_VERTICES;
 constexpr uint32_t kOptPostPass = kOptOverlayKeys | GRB_OPT_CROSSHAIR | GRB_OPT_FOG;
 
 struct RefTiles {            // the reference's tile grid (renderer.go:50-76)
-    int32_t ntx, nty;        // numTilesX, numTilesY
+    int32_t ntx, nty;        // numTilesX, numTilesY (1 or 4)
     int32_t tw, th;          // tileWidth, tileHeight
+    // calculateTileBoundaries per column / row, as floats: start and (clamped) end; NaN beyond ntx / nty
+    float sx[4], ex[4], sy[4], ey[4];
 };
 
 struct DrawArgs {
@@ -169,6 +171,7 @@ struct DrawArgs {
     int32_t tileRowBegin, tileRowEnd;  // strip, in tile rows
     // params
     Mat4 screen;
+    int32_t screenNoZ;          // screen.m[2] == 0 && screen.m[6] == 0 (NewScreenMatrix): see to_screen
     FmaConsts fma;              // run-time -0 / 1 for the packed FFMA2 products (gr_math.cuh)
     float lx, ly, lz;
     uint32_t options;

@@ -139,12 +139,11 @@ struct ScreenVert {
 //     (matrix.go:108-118), so for a finite quotient the term is +-0 and x + (+-0) == x in every
 //     later comparison and in the integer snap.  |z| <= 2^60 and |w| >= 2^-60 keep the quotient
 //     finite; anything else (and any other screen matrix) takes the literal path.
-__device__ __forceinline__ ScreenVert to_screen(const Mat4 &S, float4 p) {
+__device__ __forceinline__ ScreenVert to_screen(const Mat4 &S, bool noZ, float4 p) {
     ScreenVert s;
     s.w = p.w;
     const float aw = fabsf(p.w);
-    const bool fast = S.m[2] == 0.0f && S.m[6] == 0.0f && aw >= 8.673617e-19f && aw <= 1.1529215e18f &&
-                      fabsf(p.z) <= 1.1529215e18f;
+    const bool fast = noZ && aw >= 8.673617e-19f && aw <= 1.1529215e18f && fabsf(p.z) <= 1.1529215e18f;
     if (fast) {
         const float qx = fdiv(p.x, p.w), qy = fdiv(p.y, p.w);
         // ((m0*qx + m1*qy) + m2*qz) + m3*1 with the m2*qz = +-0 term dropped
@@ -244,20 +243,16 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
         return e;  // in no tile list: tpf 0, no record
     const float minX = fminf(fminf(s0.sx, s1.sx), s2.sx), maxX = fmaxf(fmaxf(s0.sx, s1.sx), s2.sx);
     const float minY = fminf(fminf(s0.sy, s1.sy), s2.sy), maxY = fmaxf(fmaxf(s0.sy, s1.sy), s2.sy);
-    const float Wf = (float)a.width, Hf = (float)a.height;
-    int c0 = 1 << 30, c1 = -1, r0 = 1 << 30, r1 = -1, nc = 0, nr = 0;
-    for (int c = 0; c < a.ref.ntx; c++) {   // calculateTileBoundaries (renderer.go:50-76)
-        const float sx = (float)(c * a.ref.tw);
-        float ex = fadd(sx, (float)a.ref.tw);
-        if (a.ref.ntx == 1 || ex > Wf) ex = Wf;
-        if (maxX >= sx && minX <= ex) { nc++; c0 = min(c0, c); c1 = max(c1, c); }
-    }
-    for (int r = 0; r < a.ref.nty; r++) {
-        const float sy = (float)(r * a.ref.th);
-        float ey = fadd(sy, (float)a.ref.th);
-        if (a.ref.nty == 1 || ey > Hf) ey = Hf;
-        if (maxY >= sy && minY <= ey) { nr++; r0 = min(r0, r); r1 = max(r1, r); }
-    }
+    // calculateTileBoundaries (renderer.go:50-76) is a regular grid: column c lists the triangle iff
+    // maxX >= sx[c] && minX <= ex[c].  sx grows with c and ex does not shrink, so the columns passing
+    // the first test are 0..c1, the ones failing the second 0..c0-1, and the listed ones c0..c1
+    // (bounds precomputed by the host, NaN — every comparison false — beyond the grid).
+    const RefTiles &g = a.ref;
+    const int c1 = (int)(maxX >= g.sx[0]) + (int)(maxX >= g.sx[1]) + (int)(maxX >= g.sx[2]) + (int)(maxX >= g.sx[3]) - 1;
+    const int c0 = (int)(minX > g.ex[0]) + (int)(minX > g.ex[1]) + (int)(minX > g.ex[2]) + (int)(minX > g.ex[3]);
+    const int r1 = (int)(maxY >= g.sy[0]) + (int)(maxY >= g.sy[1]) + (int)(maxY >= g.sy[2]) + (int)(maxY >= g.sy[3]) - 1;
+    const int r0 = (int)(minY > g.ey[0]) + (int)(minY > g.ey[1]) + (int)(minY > g.ey[2]) + (int)(minY > g.ey[3]);
+    const int nc = max(c1 - c0 + 1, 0), nr = max(r1 - r0 + 1, 0);
     e.tpf = nc * nr;
     if (e.tpf == 0) return e;
     if (!OVL && !(a.options & GRB_OPT_SHOW_FACES)) return e;
@@ -487,7 +482,7 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
         Emit e;
         e.valid = false;
         if (alive) {
-            e = setup_triangle<OVL>(a, to_screen(a.screen, v0), to_screen(a.screen, v1), to_screen(a.screen, v2), in0,
+            e = setup_triangle<OVL>(a, to_screen(a.screen, a.screenNoZ, v0), to_screen(a.screen, a.screenNoZ, v1), to_screen(a.screen, a.screenNoZ, v2), in0,
                                     in1, in2, tex);
             tpf = e.tpf;
             nbad = e.bad ? 1 : 0;
@@ -531,7 +526,7 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
             poly[2] = {v2, fuv.u2, fuv.v2, in2};
             count = clip_polygon(poly, tmp, a.zNear, a.zFar);
             if (count < 3) count = 0;  // Triangulate (clipping.go:47-49)
-            for (int i = 0; i < count; i++) sv[i] = to_screen(a.screen, poly[i].p);
+            for (int i = 0; i < count; i++) sv[i] = to_screen(a.screen, a.screenNoZ, poly[i].p);
             // fan (0, i+1, i+2)  (clipping.go:54-59)
             for (int i = 0; i + 2 < count; i++) {
                 const Emit e = setup_triangle<OVL>(a, sv[0], sv[i + 1], sv[i + 2], poly[0].in, poly[i + 1].in,
