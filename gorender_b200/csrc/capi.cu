@@ -88,7 +88,7 @@ struct grb_context {
 
     // workspace
     DevBuf<float4> tv;
-    DevBuf<TriRec> rec;
+    DevBuf<PackedRec> rec;
     DevBuf<TriUV> uv;
     DevBuf<uint32_t> warpCount, descCount, bigList;
     DevBuf<TileDesc> desc;
@@ -994,7 +994,7 @@ int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_r
     if (nobj) CK(ctx, cudaMemcpy(fo.data(), ctx->dFrameObjs.p + (size_t)frame * nobj, nobj * sizeof(FrameObj), cudaMemcpyDeviceToHost));
     const bool optClip = ctx->lastOptions & GRB_OPT_FRUSTUM_CLIPPING;
     int64_t k = 0;
-    std::vector<grb_triangle_rec> seg;
+    std::vector<PackedRec> seg;
     std::vector<TriUV> seguv;
     for (int32_t i = 0; i < nobj; i++) {
         if (fo[i].visibility == GRB_BOX_OUTSIDE) continue;
@@ -1009,12 +1009,15 @@ int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_r
             const size_t slot = (size_t)frame * ctx->recCap + fo[i].slotBase + (size_t)w * perWarp;
             seg.resize(cnt);
             seguv.resize(cnt);
-            CK(ctx, cudaMemcpy(seg.data(), ctx->rec.p + slot, cnt * sizeof(TriRec), cudaMemcpyDeviceToHost));
+            CK(ctx, cudaMemcpy(seg.data(), ctx->rec.p + slot, cnt * sizeof(PackedRec), cudaMemcpyDeviceToHost));
             CK(ctx, cudaMemcpy(seguv.data(), ctx->uv.p + slot, cnt * sizeof(TriUV), cudaMemcpyDeviceToHost));
             for (uint32_t j = 0; j < cnt; j++) {
                 if (seg[j].bx1 < seg[j].bx0) continue;  // slot of a face that survived the cull but draws nothing
                 if (k >= n) return fail(ctx, GRB_ERR_STATE, "record walk disagrees with the triangle counter");
-                out[k] = seg[j];
+                const PackedRec &pr = seg[j];   // storage form -> the ABI's record
+                out[k] = grb_triangle_rec{pr.x0, pr.y0, pr.x1, pr.y1, pr.x2, pr.y2, pr.w0, pr.w1, pr.w2, pr.i0, pr.i1, pr.i2,
+                                          pr.bx0, pr.by0, pr.bx1, pr.by1, pr.tex,
+                                          (uint32_t)(fo[i].slotBase + (size_t)w * perWarp + j)};  // slot == order key
                 if (out_uvs) {
                     if (seg[j].tex >= 0) std::memcpy(out_uvs + 6 * k, &seguv[j], 24);
                     else std::memset(out_uvs + 6 * k, 0, 24);

@@ -170,11 +170,31 @@ __device__ __forceinline__ void fine_stage(const WarpTris &wt, const uint32_t *r
     }
 }
 
-__device__ __forceinline__ TriRec load_rec(const TriRec *p) {
+// Raster bbox from the second 16 bytes of a record.
+struct Box { int x0, y0, x1, y1; };
+__device__ __forceinline__ Box unpack_box(int4 q1) {
+    return {(int)(int16_t)(q1.z & 0xffff), q1.z >> 16, (int)(int16_t)(q1.w & 0xffff), q1.w >> 16};
+}
+__device__ __forceinline__ Box load_box(const PackedRec *p) { return unpack_box(__ldg(reinterpret_cast<const int4 *>(p) + 1)); }
+
+// First sector of a record: snapped vertices, w, bbox — all the coverage / depth phase needs.
+__device__ __forceinline__ TriRec load_rec_geom(const PackedRec *p) {
+    const int4 q0 = __ldg(reinterpret_cast<const int4 *>(p)), q1 = __ldg(reinterpret_cast<const int4 *>(p) + 1);
     TriRec r;
-    const int4 *s = reinterpret_cast<const int4 *>(p);
-    int4 *d = reinterpret_cast<int4 *>(&r);
-    d[0] = __ldg(s); d[1] = __ldg(s + 1); d[2] = __ldg(s + 2); d[3] = __ldg(s + 3);
+    r.x0 = (int16_t)(q0.x & 0xffff); r.y0 = q0.x >> 16;
+    r.x1 = (int16_t)(q0.y & 0xffff); r.y1 = q0.y >> 16;
+    r.x2 = (int16_t)(q0.z & 0xffff); r.y2 = q0.z >> 16;
+    r.w0 = __int_as_float(q0.w); r.w1 = __int_as_float(q1.x); r.w2 = __int_as_float(q1.y);
+    const Box b = unpack_box(q1);
+    r.bx0 = (int16_t)b.x0; r.by0 = (int16_t)b.y0; r.bx1 = (int16_t)b.x1; r.by1 = (int16_t)b.y1;
+    return r;
+}
+// ... plus the shading half (intensities, texture).
+__device__ __forceinline__ TriRec load_rec(const PackedRec *p) {
+    TriRec r = load_rec_geom(p);
+    const int4 q2 = __ldg(reinterpret_cast<const int4 *>(p) + 2);
+    r.i0 = __int_as_float(q2.x); r.i1 = __int_as_float(q2.y); r.i2 = __int_as_float(q2.z);
+    r.tex = q2.w;
     return r;
 }
 
@@ -275,7 +295,7 @@ __device__ __forceinline__ void post_quad(const DrawArgs &a, int frame, int gx, 
 // One batch of up to 32 list entries of a warp: lane `lane` holds record slot `slot` when
 // `have`.  Small triangles go through the coarse / fine stages; a large one (more than kSmallArea
 // pixels inside the tile) is swept by the whole warp, one tile row at a time, lane = column.
-__device__ __forceinline__ void process_batch(bool have, uint32_t slot, const TriRec *rec, WarpTris &wt, uint32_t *ring,
+__device__ __forceinline__ void process_batch(bool have, uint32_t slot, const PackedRec *rec, WarpTris &wt, uint32_t *ring,
                                               uint32_t &qHead, uint32_t &qTail, int lane, int tileX, int tileY,
                                               int tileX1, int tileY1, unsigned long long *keys, uint32_t *largeQ,
                                               int *largeCount) {
@@ -283,7 +303,7 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
     int rows = 0;   // bbox rows of this lane's triangle inside the tile (0: nothing for the small paths)
     bool large = false, tiny = false;
     if (have) {
-        const TriRec r = load_rec(rec + slot);
+        const TriRec r = load_rec_geom(rec + slot);
         const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
         const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
         if (x0 <= x1 && y0 <= y1) {
@@ -423,7 +443,7 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
         const int src = __ffs(largeMask) - 1;
         largeMask &= largeMask - 1;
         const uint32_t s = __shfl_sync(0xffffffffu, slot, src);
-        const TriRec r = load_rec(rec + s);  // same address for every lane: one broadcast transaction
+        const TriRec r = load_rec_geom(rec + s);  // same address for every lane: one broadcast transaction
         const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
         const int x = tileX + lane;
         const int y0 = max((int)r.by0, tileY), y1 = min((int)r.by1, tileY1);
@@ -449,21 +469,20 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Tr
 
 // Block-wide pass over the queued large triangles: every thread owns 4 consecutive pixels of the
 // tile and keeps their keys in registers while it walks the queue; no atomics.
-__device__ __forceinline__ void coop_pass(const uint32_t *largeQ, int nq, const TriRec *rec, int gx, int gy, int px, int py,
+__device__ __forceinline__ void coop_pass(const uint32_t *largeQ, int nq, const PackedRec *rec, int gx, int gy, int px, int py,
                                           unsigned long long *keys) {
     unsigned long long k0 = keys[py * kTile + px], k1 = keys[py * kTile + px + 1];
     unsigned long long k2 = keys[py * kTile + px + 2], k3 = keys[py * kTile + px + 3];
     // bbox first (one 16-byte broadcast load): most threads are outside a medium triangle; the
     // next entry's bbox is fetched one iteration ahead
-    int4 bNext = __ldg(reinterpret_cast<const int4 *>(rec + largeQ[0]) + 3);
+    Box bNext = load_box(rec + largeQ[0]);
     for (int q = 0; q < nq; q++) {
         const uint32_t slot = largeQ[q];
-        const int4 b = bNext;
-        if (q + 1 < nq) bNext = __ldg(reinterpret_cast<const int4 *>(rec + largeQ[q + 1]) + 3);
-        const int bx0 = (int16_t)(b.x & 0xffff), by0 = (int16_t)(b.x >> 16);
-        const int bx1 = (int16_t)(b.y & 0xffff), by1 = (int16_t)(b.y >> 16);
+        const Box b = bNext;
+        if (q + 1 < nq) bNext = load_box(rec + largeQ[q + 1]);
+        const int bx0 = b.x0, by0 = b.y0, bx1 = b.x1, by1 = b.y1;
         if (gy < by0 || gy > by1 || gx > bx1 || gx + 3 < bx0) continue;
-        const TriRec r = load_rec(rec + slot);
+        const TriRec r = load_rec_geom(rec + slot);
         const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
         int f01 = e.a01 * gx + e.b01 * gy + e.c01;
         int f12 = e.a12 * gx + e.b12 * gy + e.c12;
@@ -524,12 +543,11 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     bool empty = nDescAll == 0;
     if (empty && nBig != 0) {
         const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
-        const TriRec *rec = a.rec + (size_t)frame * a.recCap;
+        const PackedRec *rec = a.rec + (size_t)frame * a.recCap;
         bool hit = false;
         for (uint32_t i = tid; i < nBig; i += kRasterThreads) {
-            const int4 b = __ldg(reinterpret_cast<const int4 *>(rec + big[i]) + 3);
-            const int bx0 = (int16_t)(b.x & 0xffff), by0 = (int16_t)(b.x >> 16);
-            const int bx1 = (int16_t)(b.y & 0xffff), by1 = (int16_t)(b.y >> 16);
+            const Box b = load_box(rec + big[i]);
+            const int bx0 = b.x0, by0 = b.y0, bx1 = b.x1, by1 = b.y1;
             hit |= bx0 < tileX + kTile && bx1 >= tileX && by0 < tileY + kTile && by1 >= tileY;
         }
         empty = !__syncthreads_or(hit);
@@ -555,7 +573,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     }
 
     const int tileX1 = min(tileX + kTile, a.width) - 1, tileY1 = min(tileY + kTile, a.height) - 1;
-    const TriRec *rec = a.rec + (size_t)frame * a.recCap;
+    const PackedRec *rec = a.rec + (size_t)frame * a.recCap;
     const TileDesc *desc = a.desc + ((size_t)frame * nTiles + tile) * a.descCap;
     const uint32_t nDesc = min(nDescAll, a.descCap);
 
@@ -597,9 +615,8 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                 const uint32_t i = (round - nRoundsOwn - nRoundsOv) * kDescRound + tid;
                 if (i < nBig) {
                     const uint32_t slot = big[i];
-                    const int4 b = __ldg(reinterpret_cast<const int4 *>(rec + slot) + 3);
-                    const int bx0 = (int16_t)(b.x & 0xffff), by0 = (int16_t)(b.x >> 16);
-                    const int bx1 = (int16_t)(b.y & 0xffff), by1 = (int16_t)(b.y >> 16);
+                    const Box b = load_box(rec + slot);
+                    const int bx0 = b.x0, by0 = b.y0, bx1 = b.x1, by1 = b.y1;
                     if (bx0 <= tileX1 && bx1 >= tileX && by0 <= tileY1 && by1 >= tileY) largeQ[atomicAdd(&largeCount, 1)] = slot;
                 }
                 __syncthreads();

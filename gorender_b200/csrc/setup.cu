@@ -308,10 +308,12 @@ __device__ __forceinline__ TileSpan tile_span(const TriRec &r) {
 // Writes the record (4 x 128-bit stores) and its UVs.
 __device__ __forceinline__ void store_record(const DrawArgs &a, int frame, const TriRec &rec, const TriUV &uv,
                                              uint32_t slot) {
-    TriRec *dst = a.rec + (size_t)frame * a.recCap + slot;
-    const int4 *s = reinterpret_cast<const int4 *>(&rec);
-    int4 *d = reinterpret_cast<int4 *>(dst);
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+    auto pair = [](int lo, int hi) { return (int)(((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16)); };
+    int4 *d = reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot);
+    d[0] = make_int4(pair(rec.x0, rec.y0), pair(rec.x1, rec.y1), pair(rec.x2, rec.y2), __float_as_int(rec.w0));
+    d[1] = make_int4(__float_as_int(rec.w1), __float_as_int(rec.w2), pair(rec.bx0, rec.by0), pair(rec.bx1, rec.by1));
+    d[2] = make_int4(__float_as_int(rec.i0), __float_as_int(rec.i1), __float_as_int(rec.i2), rec.tex);
+    // the last 16 bytes stay unwritten: the slot is the order key, and nobody reads them
     if (rec.tex >= 0) a.uv[(size_t)frame * a.recCap + slot] = uv;
 }
 
@@ -509,8 +511,8 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
         } else if (alive && a.warpCount) {
             // survived the cull but draws nothing (off screen / ShowFaces off / out of domain):
             // leave an empty bbox in its slot so that the stage read-back skips it
-            int4 q = make_int4(1, 0, -1, 0);  // bx0 = 1, by0 = 0, bx1 = 0, by1 = 0
-            reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot)[3] = q;
+            int4 q = make_int4(0, 0, 1, 0xffff);  // bx0 = 1, by0 = 0, bx1 = -1, by1 = 0
+            reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot)[1] = q;
         }
     } else {
         const uint32_t warpGlobal = (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
                 draw_overlays(a, frame, e.rec, e.tmax, e.ccx, e.ccy, slot);
                 if (!e.valid) {
                     // keeps its slot for the order, draws no face: empty bbox for the stage read-back
-                    if (a.warpCount) reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot)[3] = make_int4(1, 0, -1, 0);
+                    if (a.warpCount) reinterpret_cast<int4 *>(a.rec + (size_t)frame * a.recCap + slot)[1] = make_int4(0, 0, 1, 0xffff);
                     slot++;
                     continue;
                 }
