@@ -5,7 +5,7 @@
 // struct-of-arrays over the frames of a batch:
 //
 //   tv        [frames][totalVerts]        float4   clip-space vertices (K1; only when stage capture is on)
-//   rec       [frames][recCap]            PackedRec emitted triangles, 64 B   (K2 -> K5)
+//   rec       [frames][recCap]            PackedRec emitted triangles, 48 B   (K2 -> K5)
 //   uv        [frames][recCap]            TriUV    24 B, textured faces only  (K2 -> K5)
 //   warpCount [frames][nFaceBlocks*8]     u32      slots used per warp (stage capture only)
 //   descCount [frames][nTiles]            u32      descriptors appended per tile (K2 -> K5; K5 re-zeroes)
@@ -85,20 +85,19 @@ struct DrawObj {
     int32_t vertBlockBase;   // first vertex-block
 };
 
-// Storage form of a record, 64 B in two 32-byte DRAM sectors: everything the coverage / depth phase
-// of the raster kernel needs (snapped vertices as int16 — the parity domain is |coord| <= 16383 —,
-// the three w and the raster bbox) sits in the first sector, what only the shading of a winning
-// fragment needs in the second.  The gather of a tile's ~600 records per frame is the raster kernel's
-// main DRAM read: this halves it.
-struct __align__(32) PackedRec {
+// Storage form of a record, 48 B: everything the coverage / depth phase of the raster kernel needs
+// (snapped vertices as int16 — the parity domain is |coord| <= 16383 —, the three w and the raster
+// bbox) in the first 32 bytes, what only the shading of a winning fragment needs in the last 16.
+// Every byte is written (no partially written sectors, which cost a DRAM fill each), and the
+// gather of a tile's ~600 records per frame — the raster kernel's main read — moves 32 B per triangle.
+struct __align__(16) PackedRec {
     int16_t x0, y0, x1, y1, x2, y2;
     float w0, w1, w2;
     int16_t bx0, by0, bx1, by1;       // == int4 #1 .z/.w
     float i0, i1, i2;
-    int32_t tex;
-    uint32_t pad[4];                  // never written: the record's slot is its submission-order key
+    int32_t tex;                      // (the record's slot is its submission-order key: no order field)
 };
-static_assert(sizeof(PackedRec) == 64, "PackedRec must be 64 bytes");
+static_assert(sizeof(PackedRec) == 48, "PackedRec must be 48 bytes");
 
 struct __align__(16) TriRec {   // working form, == grb_triangle_rec
     int32_t x0, y0, x1, y1;

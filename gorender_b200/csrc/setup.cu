@@ -305,7 +305,7 @@ __device__ __forceinline__ TileSpan tile_span(const TriRec &r) {
     return {r.bx0 / kTile, r.by0 / kTile, r.bx1 / kTile, r.by1 / kTile};
 }
 
-// Writes the record (4 x 128-bit stores) and its UVs.
+// Writes the record (packed to 48 B, 3 x 128-bit stores) and its UVs.
 __device__ __forceinline__ void store_record(const DrawArgs &a, int frame, const TriRec &rec, const TriUV &uv,
                                              uint32_t slot) {
     auto pair = [](int lo, int hi) { return (int)(((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16)); };
@@ -313,7 +313,6 @@ __device__ __forceinline__ void store_record(const DrawArgs &a, int frame, const
     d[0] = make_int4(pair(rec.x0, rec.y0), pair(rec.x1, rec.y1), pair(rec.x2, rec.y2), __float_as_int(rec.w0));
     d[1] = make_int4(__float_as_int(rec.w1), __float_as_int(rec.w2), pair(rec.bx0, rec.by0), pair(rec.bx1, rec.by1));
     d[2] = make_int4(__float_as_int(rec.i0), __float_as_int(rec.i1), __float_as_int(rec.i2), rec.tex);
-    // the last 16 bytes stay unwritten: the slot is the order key, and nobody reads them
     if (rec.tex >= 0) a.uv[(size_t)frame * a.recCap + slot] = uv;
 }
 
