@@ -10,7 +10,7 @@ from .vecmath import (NewIdentityMatrix, NewScaleMatrix, NewTranslationMatrix, N
 from .texture import (Texture, NewColorTexture, NewImageTexture, LoadTextureFile, TextureTypeSolidColor,
                       TextureTypeImage, TextureTypeImageFast)
 from .mesh import FaceArray, Mesh, Object, NewMesh, NewObject, LoadMeshFile, boundingBox
-from .obj import LoadObjFile
+from .obj import LoadObjFile, LoadObjFileNative
 from .scene import Scene, LoadSceneFile
 from .renderer import Camera, Device, FrameBuffer, Renderer, NewFrameBuffer, NewRenderer, default_device
 

@@ -109,6 +109,12 @@ SIGNATURES = {
     "grb_mesh_new": (C.c_int32, [_VP, C.POINTER(grb_mesh_desc), c_i32_p]),
     "grb_mesh_read_derived": (C.c_int32, [_VP, C.c_int32, _VP, _VP]),
     "grb_mesh_free": (C.c_int32, [_VP, C.c_int32]),
+    "grb_obj_parse": (C.c_int32, [C.c_char_p, C.c_int32, C.POINTER(_VP), C.c_char_p, C.c_int32]),
+    "grb_obj_num_meshes": (C.c_int32, [_VP]),
+    "grb_obj_num_textures": (C.c_int32, [_VP]),
+    "grb_obj_texture_path": (C.c_char_p, [_VP, C.c_int32]),
+    "grb_obj_mesh": (C.c_int32, [_VP, C.c_int32, C.POINTER(grb_mesh_desc)]),
+    "grb_obj_free": (None, [_VP]),
     "grb_framebuffer_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_VP)]),
     "grb_framebuffer_wrap": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.POINTER(_VP)]),
     "grb_framebuffer_destroy": (C.c_int32, [_VP]),

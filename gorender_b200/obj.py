@@ -233,3 +233,66 @@ def LoadObjFile(filename: str, singleMesh: bool) -> List[Mesh]:
     if not meshes:
         raise ValueError("obj file does not have any vertices data")
     return meshes
+
+
+def LoadObjFileNative(filename: str, singleMesh: bool, device=None) -> List[Mesh]:
+    """LoadObjFile (obj.go:196-309) with the parsing done by the native library (`grb_obj_parse`,
+    csrc/objparse.cpp: one pass over the file in memory instead of a scan per line; SURVEY.md §8f
+    n4) — same meshes, bit for bit, as `LoadObjFile`.  Textures are decoded here, like in the
+    reference's host code.  With `device`, NewMesh's face normals and bounding box are computed on
+    the GPU while each mesh is uploaded (`grb_mesh_new`)."""
+    import ctypes as C
+
+    from . import _cabi
+
+    lib = _cabi.load()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.grb_obj_parse(os.fsencode(filename), int(bool(singleMesh)), C.byref(h), err, len(err))
+    if rc != 0:
+        msg = err.value.decode("utf-8", "replace")
+        if msg.startswith("open ") or msg.startswith("failed to parse material library"):
+            raise RuntimeError(msg)
+        if msg == "index out of range":
+            raise IndexError("texture vertex index out of range")
+        raise ValueError(msg)
+    try:
+        sources: List[Texture] = []
+        for i in range(lib.grb_obj_num_textures(h)):
+            path = lib.grb_obj_texture_path(h, i).decode()
+            if path == "":
+                sources.append(Texture(TextureTypeSolidColor, color=(255, 0, 255, 255)))  # obj.go:208
+            else:
+                log.info("loading texture: %s", path)
+                try:
+                    sources.append(LoadTextureFile(path))
+                except Exception as e:
+                    raise RuntimeError(f"failed to load texture: {e}")
+        meshes: List[Mesh] = []
+        for i in range(lib.grb_obj_num_meshes(h)):
+            d = _cabi.grb_mesh_desc()
+            assert lib.grb_obj_mesh(h, i, C.byref(d)) == 0
+            nv, nvn, nf = d.nv, d.nvn, d.nf
+
+            def arr(ptr, n, dtype):
+                if n == 0 or not ptr:
+                    return np.zeros(0, dtype)
+                return np.ctypeslib.as_array(ptr, (n,)).astype(dtype, copy=True)
+
+            verts = arr(d.vertices, nv * 4, np.float32).reshape(nv, 4)
+            vns = arr(d.vnormals, nvn * 4, np.float32).reshape(nvn, 4)
+            vidx = arr(d.vidx, nf * 3, np.int32).reshape(nf, 3)
+            nidx = arr(d.nidx, nf * 3, np.int32).reshape(nf, 3)
+            uvs = arr(d.uvs, nf * 6, np.float32).reshape(nf, 3, 2)
+            src = arr(d.tex, nf, np.int32)
+            # Face.Texture pointers -> the mesh's texture list in order of first use
+            used, first = np.unique(src[src >= 0], return_index=True) if nf else (np.zeros(0, np.int32), np.zeros(0, np.int64))
+            order = used[np.argsort(first)]
+            lut = np.full(len(sources) + 1, -1, np.int32)
+            lut[order] = np.arange(len(order), dtype=np.int32)
+            tex_index = lut[src] if nf else np.zeros(0, np.int32)
+            faces = FaceArray(vidx, nidx, uvs, tex_index, [sources[k] for k in order])
+            meshes.append(NewMesh(verts, vns, faces, device=device))
+        return meshes
+    finally:
+        lib.grb_obj_free(h)

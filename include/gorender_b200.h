@@ -178,6 +178,22 @@ int32_t grb_mesh_new(grb_context *ctx, const grb_mesh_desc *desc, int32_t *out_i
 int32_t grb_mesh_read_derived(grb_context *ctx, int32_t id, float *fnormals, float bbox[32]);
 int32_t grb_mesh_free(grb_context *ctx, int32_t id);
 
+/* ---- LoadObjFile's parsing (obj.go:196-309) as native host code: one pass over the file in memory,
+ *      strtof-grade float32, the reference's four face syntaxes, per-object index offsets and the
+ *      `v//vn` quirk (obj.go:77-89).  No CUDA involved (works without a device).  Textures are
+ *      not decoded here (image.Decode stays the caller's, texture.go:91-103): faces carry an index
+ *      into the file's table of texture sources — path "" is the default solid {255,0,255,255}
+ *      texture of materials without map_Kd (obj.go:208), -1 the nil texture.  grb_obj_mesh fills a
+ *      grb_mesh_desc whose arrays stay valid until grb_obj_free; fnormals is NULL and bbox unset:
+ *      hand it to grb_mesh_new (NewMesh on the device) or derive them on the host. */
+typedef struct grb_obj grb_obj;
+int32_t grb_obj_parse(const char *filename, int32_t single_mesh, grb_obj **out, char *err, int32_t err_cap);
+int32_t grb_obj_num_meshes(const grb_obj *obj);
+int32_t grb_obj_num_textures(const grb_obj *obj);
+const char *grb_obj_texture_path(const grb_obj *obj, int32_t i);
+int32_t grb_obj_mesh(const grb_obj *obj, int32_t i, grb_mesh_desc *desc);
+void grb_obj_free(grb_obj *obj);
+
 /* ---- framebuffer: NewFrameBuffer (rasterizer.go:15-23) ------------------
  * `frames` device frames of RGBA8 colour + f32 depth each (frames > 1 for
  * frame-parallel batches).  Clear + DotGrid (rasterizer.go:36-52) are
