@@ -518,7 +518,10 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     __shared__ uint32_t slotList[kSlotWin];
     __shared__ uint32_t warpSums[kRasterThreads / 32];
     __shared__ uint32_t largeQ[kLargeQueue];
-    __shared__ int largeCount;
+    // Two counters used alternately (one per window of entries): the one a window does NOT use is
+    // re-zeroed behind that window's first barrier, so a reset never races with the reads of the
+    // window before.
+    __shared__ int largeCount[2];
 
     const int tid = threadIdx.x;
     const int nTiles = a.ntx * a.nty;
@@ -578,6 +581,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     const uint32_t nDesc = min(nDescAll, a.descCap);
 
     for (int i = tid; i < kTilePix; i += kRasterThreads) keys[i] = kBackgroundKey;
+    if (tid < 2) largeCount[tid] = 0;
     __syncthreads();
     if (tid == 0) *descCount = 0;  // ready for the next draw (nobody else reads this tile's counter)
 
@@ -588,6 +592,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
         WarpTris &wt = tris[warp];
         uint32_t *ring = fragRing[warp];
         uint32_t qHead = 0, qTail = 0;  // warp-uniform
+        uint32_t win = 0;               // windows / big rounds so far (block-uniform): picks the large-triangle counter
         const OverflowDesc *ov = a.overflow + (size_t)frame * a.recCap * kMaxBinsPerTri;
         const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
         // Rounds of up to 256 descriptors: first the tile's in-place list, then (rarely) the frame's
@@ -610,19 +615,20 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
             } else {
                 // big-list entries skip the expansion: whatever overlaps the tile goes straight to
                 // the block-wide pass (256 entries per round never overflow the queue)
-                if (tid == 0) largeCount = 0;
-                __syncthreads();
+                int *counter = &largeCount[win & 1];
                 const uint32_t i = (round - nRoundsOwn - nRoundsOv) * kDescRound + tid;
                 if (i < nBig) {
                     const uint32_t slot = big[i];
                     const Box b = load_box(rec + slot);
                     const int bx0 = b.x0, by0 = b.y0, bx1 = b.x1, by1 = b.y1;
-                    if (bx0 <= tileX1 && bx1 >= tileX && by0 <= tileY1 && by1 >= tileY) largeQ[atomicAdd(&largeCount, 1)] = slot;
+                    if (bx0 <= tileX1 && bx1 >= tileX && by0 <= tileY1 && by1 >= tileY) largeQ[atomicAdd(counter, 1)] = slot;
                 }
                 __syncthreads();
-                const int nqBig = largeCount;
+                if (tid == 0) largeCount[(win + 1) & 1] = 0;
+                const int nqBig = *counter;
                 if (nqBig) coop_pass(largeQ, nqBig, rec, gx, gy, px, py, keys);
                 __syncthreads();
+                win++;
                 continue;
             }
             // -- block-wide exclusive scan of the triangle counts: the slots of this thread's
@@ -651,8 +657,8 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
             // -- windows of kSlotWin entries: every thread scatters its descriptor's record slots
             //    into the shared list (one store per triangle, no searching), then the warps take
             //    32 consecutive entries at a time
-            for (uint32_t win0 = 0; win0 < total; win0 += kSlotWin) {
-                if (tid == 0) largeCount = 0;
+            for (uint32_t win0 = 0; win0 < total; win0 += kSlotWin, win++) {
+                int *counter = &largeCount[win & 1];
                 if (first < win0 + kSlotWin && first + cnt > win0) {
                     uint32_t m = d.mask, pos = first - win0;  // wraps below the window: fails the range test
                     while (m) {
@@ -665,6 +671,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                     }
                 }
                 __syncthreads();
+                if (tid == 0) largeCount[(win + 1) & 1] = 0;
                 const uint32_t nWin = min(total - win0, (uint32_t)kSlotWin);
                 const uint32_t nBatches = (nWin + 31) / 32;
                 for (uint32_t b = warp; b < nBatches; b += kWarps) {
@@ -672,11 +679,11 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                     const bool have = e < nWin;
                     const uint32_t slot = have ? slotList[e] : 0u;
                     process_batch(have, slot, rec, wt, ring, qHead, qTail, lane, tileX, tileY, tileX1, tileY1, keys, largeQ,
-                                  &largeCount);
+                                  counter);
                 }
                 __syncthreads();
                 // -- large triangles found in this window
-                const int nq = min(largeCount, kLargeQueue);
+                const int nq = min(*counter, kLargeQueue);
                 if (nq) {
                     coop_pass(largeQ, nq, rec, gx, gy, px, py, keys);
                     __syncthreads();
