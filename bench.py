@@ -439,9 +439,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     ntiles = ((WIDTH + 31) // 32) * ((HEIGHT + 31) // 32)
     alg = {   # algorithmic bytes per frame of each kernel
         "transform": 0.0,                                          # fused into setup (stage capture only)
-        "setup": 48.0 * nfaces + 16.0 * tris + 64.0 * tris + 8.0 * tris / 6.0,   # corners in; normals, records, descriptors
+        "setup": 48.0 * nfaces + 16.0 * tris + 48.0 * tris + 8.0 * tris / 6.0,   # corners in; normals, 48-byte records, descriptors
         "bin_scan": 0.0, "bin_fill": 0.0,                          # no such kernels any more
-        "raster": 8.0 * WIDTH * HEIGHT + 64.0 * tris + 8.0 * tris / 6.0 + 4.0 * ntiles,  # fb out; records, descriptors, counters in
+        "raster": 8.0 * WIDTH * HEIGHT + 48.0 * tris + 8.0 * tris / 6.0 + 4.0 * ntiles,  # fb out; records, descriptors, counters in
     }
     ktimes = {k: v for k, v in ktimes.items() if alg.get(k, 0.0) > 0.0}
     dom = max(ktimes, key=lambda k: ktimes[k])
