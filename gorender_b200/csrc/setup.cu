@@ -13,7 +13,7 @@
 //    triangle records plus the device-tile bin counts.
 //
 // One thread per face; a block owns kFaceBlock consecutive faces of one
-// object and its warps are independent (no block barrier).  The emitted
+// object and its warps are independent (no block barrier, no shared memory).  The emitted
 // triangles of a warp are compacted with a ballot and stored at statically
 // assigned record slots: slot = object base + warp index * slots-per-warp +
 // rank in warp.  Slot order is submission order (object, face, fan), so the
@@ -353,11 +353,6 @@ __device__ __forceinline__ float light_intensity(const Mat4P &world, float4 n, f
 
 // ---------------------------------------------------------------- K2
 
-// Face data handed from the cull phase to the emit phase of a block through shared memory.
-struct __align__(16) StagedFace {
-    float4 v0, v1, v2;       // clip-space vertices
-};
-
 // OVL: the instantiation that also draws the ShowEdges / ShowVertices overlays (as event keys into
 // a.ovl); the frame path proper is the OVL = false one.
 template <bool CLIP, bool OVL>
@@ -403,52 +398,18 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
 
     uint32_t slot;  // record slot(s) of this thread's face: static, in submission order
     if constexpr (!CLIP) {
-        // Surviving faces (40 % of C3's) are compacted across the block so that the expensive part
-        // below — 12 IEEE divides, a square root, the tile tests, the record stores — runs in
-        // full warps; warps left without work retire here.
-        __shared__ StagedFace staged[kFaceBlock];
-        __shared__ uint32_t stagedMeta[kFaceBlock][2];   // face index, record slot
-        __shared__ uint32_t warpAlive[kWarpsPerFaceBlock];
+        // Warps are independent (no block barrier, no shared memory): a warp whose faces are all culled
+        // retires here, the others carry their survivors through phase 2 where they are.  (Compacting
+        // the survivors of a block across its warps through shared memory was measured on C1, C3 and
+        // C4: no gain — culling is spatially coherent, most warps are all-alive or all-dead already.)
         const unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
         const uint32_t warpGlobal = (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock;
         const uint32_t slot0 = fo.slotBase + ((uint32_t)(fb - ob.faceBlockBase) * kWarpsPerFaceBlock + warpInBlock) * kWarpSlots;
-        if (lane == 0) {
-            warpAlive[warpInBlock] = __popc(aliveMask);
-            // slots [slot0, slot0 + count) are in use; the ones whose triangle turns out to be
-            // invisible are marked with an empty bbox in phase 2 (only the stage read-back looks)
-            if (a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = __popc(aliveMask);
-        }
-        __syncthreads();
-        uint32_t base = 0, nAlive = 0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerFaceBlock; w++) {
-            const uint32_t c = warpAlive[w];
-            if (w < (int)warpInBlock) base += c;
-            nAlive += c;
-        }
-        if (nAlive == 0) return;
+        // slots [slot0, slot0 + count) are in use; the ones whose triangle turns out to be
+        // invisible are marked with an empty bbox in phase 2 (only the stage read-back looks)
+        if (lane == 0 && a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = __popc(aliveMask);
+        if (aliveMask == 0) return;  // whole warp culled
         slot = slot0 + __popc(aliveMask & ltMask);
-        // Compaction pays only when it frees whole warps (block-uniform decision): a block whose
-        // survivors still need all 8 warps keeps every face where it is.
-        if (nAlive <= kFaceBlock - 32) {
-            if (alive) {
-                const uint32_t rank = __popc(aliveMask & ltMask);
-                staged[base + rank] = {v0, v1, v2};
-                stagedMeta[base + rank][0] = (uint32_t)f;
-                stagedMeta[base + rank][1] = slot;
-            }
-            __syncthreads();
-            alive = threadIdx.x < nAlive;
-            if (warpInBlock * 32 >= nAlive) return;  // whole warp idle
-            if (alive) {
-                const StagedFace sf = staged[threadIdx.x];
-                v0 = sf.v0; v1 = sf.v1; v2 = sf.v2;
-                f = (int)stagedMeta[threadIdx.x][0];
-                slot = stagedMeta[threadIdx.x][1];
-            }
-        } else if (aliveMask == 0) {
-            return;  // whole warp culled
-        }
     }
 
     // ------------------------------------------------------------ phase 2: light, project, emit
