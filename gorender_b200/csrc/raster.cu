@@ -302,6 +302,8 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Pa
     const unsigned ltMask = (1u << lane) - 1u;
     int rows = 0;   // bbox rows of this lane's triangle inside the tile (0: nothing for the small paths)
     bool large = false, tiny = false;
+    Edges e = {};          // this lane's triangle: kept in registers for the tiny path
+    int ox = 0, oy = 0, obw = 0;   // its clipped bbox origin (absolute) and width
     if (have) {
         const TriRec r = load_rec_geom(rec + slot);
         const int x0 = max((int)r.bx0, tileX), x1 = min((int)r.bx1, tileX1);
@@ -309,7 +311,8 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Pa
         if (x0 <= x1 && y0 <= y1) {
             const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
             if (bw <= kSmallWidth && bw * bh <= kSmallArea) {
-                const Edges e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+                e = make_edges(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+                ox = x0; oy = y0; obw = bw;
                 wt.a01[lane] = e.a01; wt.b01[lane] = e.b01; wt.c01[lane] = e.c01;
                 wt.a12[lane] = e.a12; wt.b12[lane] = e.b12; wt.c12[lane] = e.c12;
                 wt.a20[lane] = e.a20; wt.b20[lane] = e.b20; wt.c20[lane] = e.c20;
@@ -328,14 +331,12 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Pa
     //      + column); the fragments of the 32 masks then go into the ring
     uint32_t cover = 0u;
     if (tiny) {
-        const uint32_t box = wt.box[lane];
-        const int bw = (int)(box >> 10), lx0 = (int)(box & 31u), ly0 = (int)((box >> 5) & 31u);
-        const int x = tileX + lx0, y = tileY + ly0;
-        const int a01 = wt.a01[lane], a12 = wt.a12[lane], a20 = wt.a20[lane];
-        const int b01 = wt.b01[lane], b12 = wt.b12[lane], b20 = wt.b20[lane];
-        int r01 = a01 * x + b01 * y + wt.c01[lane];
-        int r12 = a12 * x + b12 * y + wt.c12[lane];
-        int r20 = a20 * x + b20 * y + wt.c20[lane];
+        const int bw = obw, x = ox, y = oy;
+        const int a01 = e.a01, a12 = e.a12, a20 = e.a20;
+        const int b01 = e.b01, b12 = e.b12, b20 = e.b20;
+        int r01 = a01 * x + b01 * y + e.c01;
+        int r12 = a12 * x + b12 * y + e.c12;
+        int r20 = a20 * x + b20 * y + e.c20;
         // all 16 pixels of the 4 x 4 block at the bbox origin, no loop control; the ones outside the
         // bbox (or the tile) are masked off afterwards
 #pragma unroll
@@ -353,8 +354,7 @@ __device__ __forceinline__ void process_batch(bool have, uint32_t slot, const Pa
         rows = 0;  // not for the row path below
     }
     {
-        const uint32_t box = wt.box[lane];
-        const uint32_t origin = ((uint32_t)lane << 10) | (box & 1023u);  // t | ly0 << 5 | lx0
+        const uint32_t origin = ((uint32_t)lane << 10) | ((uint32_t)(oy - tileY) << 5) | (uint32_t)(ox - tileX);  // t | ly0 << 5 | lx0
         unsigned pending = __ballot_sync(0xffffffffu, cover != 0);
         while (pending) {
             const bool emit = cover != 0;

@@ -536,10 +536,8 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
     }
 
     // TPF (renderer.go:436-441) and diagnostics: one atomic per warp
-    for (int d = 16; d > 0; d >>= 1) {
-        tpf += __shfl_xor_sync(0xffffffffu, tpf, d);
-        nbad += __shfl_xor_sync(0xffffffffu, nbad, d);
-    }
+    tpf = (int)__reduce_add_sync(0xffffffffu, (unsigned)tpf);     // REDUX: one instruction each
+    nbad = (int)__reduce_add_sync(0xffffffffu, (unsigned)nbad);
     if (lane == 0) {
         if (tpf) atomicAdd(&a.counters[frame].tpf, (unsigned long long)tpf);
         if (nbad) atomicAdd(&a.counters[frame].outOfDomain, (uint32_t)nbad);
