@@ -513,6 +513,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE line, the JSON: native libraries that write to file descriptor 1 on their own
+    # (NCCL prints its version banner there) are sent to stderr for the whole run, and print() keeps the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
