@@ -159,6 +159,23 @@ def big_triangles(w=1280, h=720, **opt):
                     g.Camera(Position=(0, 0, 4.0)), opt)
 
 
+def offscreen_no_clip(w=640, h=360, **opt):
+    """FrustumClipping off with objects hanging over every screen edge (all in front of the camera, so
+    |snapped coordinate| stays far inside the 16383 domain): negative and > width coordinates reach the
+    tile test, the raster bbox clamps and — with overlays — FrameBuffer.Pixel's linear-index wrap."""
+    suz = workloads.suzanne()
+    objs = [
+        _obj(suz, t=(-3.4, 0.3, 0.0), r=(0, 0.5, 0)),     # over the left edge
+        _obj(suz, t=(3.5, -0.2, 0.5), r=(0, -0.4, 0)),    # over the right edge
+        _obj(suz, t=(0.3, 2.0, 0.0), r=(0.3, 0, 0)),      # over the top
+        _obj(suz, t=(-0.4, -2.1, 1.0), r=(-0.2, 0.2, 0)),  # over the bottom
+        _obj(workloads.cube(), t=(0, 0, -2.0), r=(0.4, 0.3, 0.1)),
+    ]
+    o = {"FrustumClipping": False}
+    o.update(opt)
+    return SceneDef(w, h, objs, geometry.default_camera(), o)
+
+
 PINNED: Dict[str, Callable[[], SceneDef]] = {
     "c1_suzanne_720p": c1,
     "c1_suzanne_800x600": lambda: c1(800, 600),
@@ -186,6 +203,10 @@ PINNED: Dict[str, Callable[[], SceneDef]] = {
     "big_triangles": big_triangles,
     "no_faces": lambda: c1(640, 360, ShowFaces=False),
     "no_clipping_inside": lambda: c1(640, 360, FrustumClipping=False),
+    "offscreen_no_clip": offscreen_no_clip,
+    "offscreen_no_clip_serial": lambda: SceneDef(333, 211, offscreen_no_clip().objects, geometry.default_camera(),
+                                                 {"FrustumClipping": False}, parallel=False),
+    "offscreen_no_clip_wire": lambda: offscreen_no_clip(ShowEdges=True, ShowVertices=True),
     # overlays and post passes (renderer.go:191-216, 476-480)
     "wire_c1": lambda: c1(640, 360, ShowEdges=True),
     "wire_only_c1": lambda: c1(640, 360, ShowEdges=True, ShowFaces=False),

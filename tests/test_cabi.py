@@ -62,3 +62,10 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle_binding" not in text and "liboracle" not in text and "gorender_oracle" not in text, f
+
+
+def test_graft_entry_build():
+    """The driver's "does it build" check: compiles (or finds up to date) every native piece and loads the library."""
+    import __graft_entry__ as ge
+
+    ge.build()
