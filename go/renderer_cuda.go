@@ -207,6 +207,9 @@ func (r *Renderer) Draw(objects []*Object, camera *Camera) {
 	p.z_near, p.z_far = C.float(r.zNear), C.float(r.zFar)
 	p.ref_tiles = C.int32_t(r.numTiles) // 16 (parallel) or 1
 	p.row_begin, p.row_end = 0, 0
+	// GRB_OPT_FOG is never set (the Fog call is commented out at renderer.go:479); its arguments are the ones written there
+	p.fog_start, p.fog_end = 0.100, 0.033
+	p.fog_color = [4]C.uint8_t{100, 100, 100, 255}
 
 	var stats C.grb_frame_stats
 	var objPtr *C.grb_object

@@ -145,7 +145,10 @@ struct WarpTris {            // one per warp, 32 triangles
     uint32_t box[32];        // local x0 | local y0 << 5 | bw << 10
 };
 constexpr int kFragRing = 64;
-constexpr int kLargeQueue = 1024;  // large triangles a block queues per window before falling back to warp sweeps
+#ifndef GRB_LARGEQ
+#define GRB_LARGEQ 1024
+#endif
+constexpr int kLargeQueue = GRB_LARGEQ;  // large triangles a block queues per window before falling back to warp sweeps
 constexpr int kDescRound = 256;    // descriptors expanded per round (one per thread)
 constexpr int kSlotWin = GRB_SLOTWIN;      // record slots of a round held in shared memory at a time
 
@@ -678,6 +681,10 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                     const uint32_t e = b * 32 + lane;
                     const bool have = e < nWin;
                     const uint32_t slot = have ? slotList[e] : 0u;
+                    {   // the geometry sector of this warp's next batch goes to L1 one batch ahead of its use (-2 %)
+                        const uint32_t en = e + kWarps * 32;
+                        if (en < nWin) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + slotList[en]));
+                    }
                     process_batch(have, slot, rec, wt, ring, qHead, qTail, lane, tileX, tileY, tileX1, tileY1, keys, largeQ,
                                   counter);
                 }
