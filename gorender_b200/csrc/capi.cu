@@ -541,7 +541,7 @@ int32_t grb_context_destroy(grb_context *ctx) {
         if (t.pixels) cudaFree(t.pixels);
     void *bufs[] = {ctx->dMeshes.p, ctx->dTextures.p, ctx->dObjs.p, ctx->dVblk.p, ctx->dFblk.p, ctx->dFrameObjs.p,
                     ctx->tv.p, ctx->rec.p, ctx->uv.p, ctx->warpCount.p, ctx->descCount.p, ctx->desc.p, ctx->overflow.p,
-                    ctx->bigList.p, ctx->counters.p, ctx->seam.p};
+                    ctx->bigList.p, ctx->counters.p, ctx->seam.p, ctx->ovl.p};
     for (void *p : bufs)
         if (p) cudaFree(p);
     for (int i = 0; i < kStagingRing; i++) {
