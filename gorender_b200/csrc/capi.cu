@@ -710,14 +710,17 @@ int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, 
             if ((r = dev_alloc(ctx, (size_t)d->nf, &f4, m.allocs))) goto bad;
             m.dev.cn[k] = f4;
         }
-        pa.cn[k] = f4;
+        pa.cn[k] = const_cast<float4 *>(m.dev.cn[k]);
     }
     if ((r = dev_alloc(ctx, (size_t)8, &scratch, m.allocs))) goto bad;
     pa.verts = m.dev.verts; pa.vnormals = m.dev.vnormals; pa.vidx = m.dev.vidx; pa.nidx = m.dev.nidx;
     pa.nv = d->nv; pa.nvn = d->nvn; pa.nf = d->nf;
     pa.error = reinterpret_cast<int *>(scratch + 7);
     {
-        cudaError_t e = cudaMemcpyAsync(scratch, scratchInit, sizeof(scratchInit), cudaMemcpyHostToDevice, s);
+        // cudaMemcpy from pageable memory may return once the data is staged: make sure the uploads above
+        // have landed before a kernel on the context's (non-default) stream reads them
+        cudaError_t e = cudaStreamSynchronize(cudaStreamLegacy);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(scratch, scratchInit, sizeof(scratchInit), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) {
             launch_mesh_prepare(pa, s);
             if (derive) launch_bbox(m.dev.verts, d->nv, scratch, s);
