@@ -12,7 +12,10 @@
  * image, so it cannot be run here either.  The oracle is exact by
  * construction (IEEE-754 binary32 + - * / sqrt and integer arithmetic in the
  * reference's order, built with -ffp-contract=off), but nothing produced by
- * the Go binary anchors it.
+ * the Go binary anchors it.  What does: a second restatement of the same Go functions in plain
+ * Python (oracle/py_project.py, oracle/py_raster.py) that this one must equal bit for bit on small
+ * scenes (tests/test_py_raster.py), the reference's C prototype of the batch transform compiled
+ * unmodified (oracle/_ref), the counts of SURVEY.md §8c and the committed SHA-256 pins.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product path
