@@ -455,6 +455,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "ncu": ({"file": ncu["file"], "issue_active_pct": ncu["issue_active_pct"],
                  "sm_throughput_pct": ncu["sm_throughput_pct"], "dram_throughput_pct": ncu["dram_throughput_pct"],
                  "warp_instructions_per_launch": ncu["warp_instructions"],
+                 "fp32_pipe_fma_pct": ncu.get("fp32_pipe_fma_pct"), "l1_hit_pct": ncu.get("l1_hit_pct"),
                  "note": "the path is instruction-issue bound, not HBM bound: issue slots active vs DRAM % of peak"}
                 if ncu else None),
         "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": ktimes[dom],
