@@ -5,8 +5,8 @@
 // Host work per draw is what the reference also does once per object per
 // frame and is not per-vertex: BoxVisibility of the 8 bounding-box corners
 // (renderer.go:268-275, clipping.go:131-154).  Everything per-vertex,
-// per-face and per-pixel runs in the five kernels (kernels.h).  There is no
-// CPU rendering path in this library.
+// per-face and per-pixel runs in the kernels of kernels.h (two per batch of
+// frames: setup and raster).  There is no CPU rendering path in this library.
 
 #include <algorithm>
 #include <cstdio>
@@ -988,7 +988,7 @@ int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_r
     if (capacity < n) return fail(ctx, GRB_ERR_INVALID, "output too small");
     if (n == 0) return GRB_OK;
     // records sit in per-warp segments in submission order (setup.cu); walk them with the
-    // per-warp counts, exactly as bin_fill_kernel does
+    // per-warp slot counts
     const int32_t nobj = ctx->lastNobj;
     const size_t nWarps = (size_t)ctx->nFaceBlocks * kWarpsPerFaceBlock;
     std::vector<uint32_t> wc(nWarps);

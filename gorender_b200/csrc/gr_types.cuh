@@ -5,10 +5,10 @@
 // struct-of-arrays over the frames of a batch:
 //
 //   tv        [frames][totalVerts]        float4   clip-space vertices (K1; only when stage capture is on)
-//   rec       [frames][recCap]            PackedRec emitted triangles, 48 B   (K2 -> K5)
-//   uv        [frames][recCap]            TriUV    24 B, textured faces only  (K2 -> K5)
+//   rec       [frames][recCap]            PackedRec emitted triangles, 48 B   (K2 -> K3)
+//   uv        [frames][recCap]            TriUV    24 B, textured faces only  (K2 -> K3)
 //   warpCount [frames][nFaceBlocks*8]     u32      slots used per warp (stage capture only)
-//   descCount [frames][nTiles]            u32      descriptors appended per tile (K2 -> K5; K5 re-zeroes)
+//   descCount [frames][nTiles]            u32      descriptors appended per tile (K2 -> K3; K3 re-zeroes)
 //   desc      [frames][nTiles][descCap]   TileDesc per-tile triangle lists, 8 B per (warp, tile) group
 //   overflow  [frames][kMaxBinsPerTri*recCap] OverflowDesc  descriptors beyond descCap (rare)
 //   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles

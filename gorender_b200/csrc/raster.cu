@@ -1,4 +1,4 @@
-// raster.cu — K5: the per-tile rasteriser.  Replaces FrameBuffer.Clear /
+// raster.cu — K3: the per-tile rasteriser.  Replaces FrameBuffer.Clear /
 // DotGrid / Triangle (rasterizer.go:36-52, 90-183), colorIntensity (:81-88),
 // Texture.Sample (texture.go:69-89) and renderTile (renderer.go:219-223).
 //

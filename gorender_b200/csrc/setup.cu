@@ -9,8 +9,8 @@
 //    gather, backface cull (:246-250), lighting (:326-346), Sutherland–Hodgman
 //    frustum clip (clipping.go:167-236), perspective divide + viewport
 //    (:361-370), integer snap (:182-184), the reference's tile-list membership
-//    rule (:226-244) and TPF, then a block-ordered compaction of the emitted
-//    triangle records plus the device-tile bin counts.
+//    rule (:226-244) and TPF, then the emitted triangle's 48-byte record and
+//    its entry in the device-tile lists.
 //
 // One thread per face; a block owns kFaceBlock consecutive faces of one
 // object and its warps are independent (no block barrier, no shared memory).  The emitted
