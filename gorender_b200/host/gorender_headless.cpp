@@ -31,7 +31,7 @@ static void printMatrix(const char *name, const Matrix &m) {
 
 int main(int argc, char **argv) {
     int width = 1280, height = 720, frames = 100, start = 0;
-    bool matricesOnly = false, texDump = false, async = false;
+    bool matricesOnly = false, texDump = false, async = false, native = false;
     // the option hot-keys of main.go:255-272 as flags
     bool edges = false, vertices = false, noFaces = false, crossHair = false, noCull = false, noLight = false, flat = false;
     std::string ppm, raw, file;
@@ -47,6 +47,7 @@ int main(int argc, char **argv) {
         else if (a == "-matrices") matricesOnly = true;
         else if (a == "-texdump") texDump = true;
         else if (a == "-async") async = true;
+        else if (a == "-native") native = true;   // native OBJ parser + NewMesh on the device
         else if (a == "-edges") edges = true;
         else if (a == "-vertices") vertices = true;
         else if (a == "-nofaces") noFaces = true;
@@ -69,7 +70,8 @@ int main(int argc, char **argv) {
             return 0;
         }
         Scene scene;
-        for (auto &m : LoadMeshFile(file, false)) scene.Objects.push_back(NewObject(m));  // main.go:155-165
+        if (!native || matricesOnly)
+            for (auto &m : LoadMeshFile(file, false)) scene.Objects.push_back(NewObject(m));  // main.go:155-165
         Camera camera{{0, 0, 5}, {0, 0, -1}, {0, 1, 0}};                                   // main.go:192-196
         for (int k = 0; k < start; k++)
             for (auto &o : scene.Objects) o->Rotation.Y += 0.01f;
@@ -93,6 +95,11 @@ int main(int argc, char **argv) {
         }
 
         Device dev(0);
+        if (native) {   // the same scene through grb_obj_parse + grb_mesh_new
+            for (auto &m : dev.LoadObjFileNative(file, false)) scene.Objects.push_back(NewObject(m));
+            for (int k = 0; k < start; k++)
+                for (auto &o : scene.Objects) o->Rotation.Y += 0.01f;
+        }
         FrameBuffer fb(dev, width, height);
         Renderer renderer(fb);
         renderer.ShowEdges = edges;

@@ -561,6 +561,45 @@ public:
         return m;
     }
 
+    // LoadObjFile (obj.go:196-309) with the parsing done by the library's native parser (grb_obj_parse) and
+    // NewMesh done on the device: file -> GPU without a per-line Sscanf or a per-face host loop.  Textures are
+    // decoded here, as in the reference's host code.  Same meshes, bit for bit, as LoadObjFile + NewMesh.
+    std::vector<MeshPtr> LoadObjFileNative(const std::string &filename, bool singleMesh) {
+        grb_obj *obj = nullptr;
+        char err[512] = {0};
+        if (grb_obj_parse(filename.c_str(), singleMesh ? 1 : 0, &obj, err, (int32_t)sizeof(err)) != GRB_OK)
+            throw std::runtime_error(err);
+        struct Guard { grb_obj *o; ~Guard() { grb_obj_free(o); } } guard{obj};
+        std::vector<TexturePtr> sources;
+        for (int32_t i = 0; i < grb_obj_num_textures(obj); i++) {
+            const std::string path = grb_obj_texture_path(obj, i);
+            if (path.empty()) sources.push_back(NewColorTexture(255, 0, 255, 255));   // obj.go:208
+            else {
+                try { sources.push_back(LoadTextureFile(path)); }
+                catch (const std::exception &e) { throw std::runtime_error(std::string("failed to load texture: ") + e.what()); }
+            }
+        }
+        std::vector<MeshPtr> meshes;
+        for (int32_t i = 0; i < grb_obj_num_meshes(obj); i++) {
+            grb_mesh_desc d{};
+            check(grb_obj_mesh(obj, i, &d), "grb_obj_mesh");
+            std::vector<Vec4> vertices(d.nv), normals(d.nvn);
+            for (int32_t k = 0; k < d.nv; k++) vertices[k] = {d.vertices[4 * k], d.vertices[4 * k + 1], d.vertices[4 * k + 2], d.vertices[4 * k + 3]};
+            for (int32_t k = 0; k < d.nvn; k++) normals[k] = {d.vnormals[4 * k], d.vnormals[4 * k + 1], d.vnormals[4 * k + 2], d.vnormals[4 * k + 3]};
+            std::vector<Face> faces(d.nf);
+            for (int32_t f = 0; f < d.nf; f++) {
+                for (int k = 0; k < 3; k++) {
+                    faces[f].VertexIndices[k] = d.vidx[3 * f + k];
+                    faces[f].NormalIndices[k] = d.nidx[3 * f + k];
+                    faces[f].UVs[k] = {d.uvs[6 * f + 2 * k], d.uvs[6 * f + 2 * k + 1]};
+                }
+                if (d.tex[f] >= 0) faces[f].Texture = sources[d.tex[f]];
+            }
+            meshes.push_back(NewMesh(std::move(vertices), std::move(normals), std::move(faces)));
+        }
+        return meshes;
+    }
+
 private:
     int32_t uploadMesh(const MeshPtr &m, bool derive) {
         const size_t nf = m->Faces.size();

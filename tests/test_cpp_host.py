@@ -129,6 +129,10 @@ def test_headless_driver_matches_python_path(tmp_path, device):
     raw2 = tmp_path / "out_async.bin"
     run("-w", 640, "-h", 360, "-frames", 3, "-async", "-raw", raw2, obj)
     assert np.array_equal(np.fromfile(raw2, dtype=np.uint8), blob)
+    # the same file through the native OBJ parser and NewMesh on the device
+    raw4 = tmp_path / "out_native.bin"
+    out4 = run("-w", 640, "-h", 360, "-frames", 3, "-native", "-raw", raw4, obj)
+    assert np.array_equal(np.fromfile(raw4, dtype=np.uint8), blob) and f"tpf={r.TPF} " in out4
     # the option hot-keys (main.go:255-272) as flags: wireframe + vertex marks + crosshair
     raw3 = tmp_path / "out_wire.bin"
     run("-w", 640, "-h", 360, "-frames", 3, "-edges", "-vertices", "-crosshair", "-raw", raw3, obj)
