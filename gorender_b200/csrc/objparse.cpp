@@ -17,8 +17,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gorender_b200.h"
@@ -211,86 +214,111 @@ bool parse_mtl(const std::string &filename, std::vector<Material> &mats, std::st
     return true;
 }
 
+// ---- the parser: one serial pass that classifies the lines and runs the statements whose effect depends on
+// file order (`mtllib`, `usemtl`, `o`), then the bulk — the floats of every `v` / `vt` / `vn` line and the
+// indices of every `f` line — parsed by a few threads.  An `o` statement starts a new mesh when the current one
+// has vertices (obj.go:257-262), and the index offsets of a mesh (obj.go:31-40) are simply the numbers of `v`,
+// `vt` and `vn` lines before it, so no parsed value is needed to place any other.  The first error in file
+// order wins, as it would in the reference's line-by-line loop.
+
+struct Segment {             // one mesh: the lines between two effective `o` statements
+    size_t v0, vt0, vn0, f0;   // first v / vt / vn / f line (global numbering) == ObjContext offsets
+    size_t v1, vt1, vn1, f1;   // one past the last
+};
+
+struct FaceLine {
+    Span line;
+    size_t ordinal;          // statement number in the file (for "first error wins")
+    int32_t tex, seg;
+};
+struct FloatLine {
+    Span line;
+    size_t ordinal;
+};
+
+struct ErrorSlot {           // smallest ordinal wins
+    std::mutex mu;
+    size_t ordinal = SIZE_MAX;
+    std::string msg;
+    void report(size_t ord, const std::string &m) {
+        std::lock_guard<std::mutex> g(mu);
+        if (ord < ordinal) { ordinal = ord; msg = m; }
+    }
+};
+
+template <typename Fn> void parallel_for(size_t n, Fn fn) {
+    const size_t kMinPerThread = 20000;
+    size_t threads = std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), n / kMinPerThread);
+    if (threads <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < threads; t++) pool.emplace_back([=] { fn(n * t / threads, n * (t + 1) / threads); });
+    for (auto &th : pool) th.join();
+}
+
+// parseFace (obj.go:60-151) for one line of segment `sg`; tv = all parsed texture vertices (u, v), global numbering.
+// Returns an empty string or the error.
+std::string parse_face(Span line, const Segment &sg, const float *tv, int32_t *vidx, int32_t *nidx, float *uvs) {
+    if (count_char(line, ' ') != 3) return "mesh is not triangulated";
+    const long vOff = (long)sg.v0, vtOff = (long)sg.vt0, vnOff = (long)sg.vn0;
+    const int slashes = count_char(line, '/');
+    long v[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, vn[3] = {0, 0, 0};
+    const char *p = line.b + 2, *e = line.e;
+    bool ok = true, has_vt = false;
+    if (count_double_slash(line) == 3) {
+        long n[3] = {0, 0, 0};
+        for (int k = 0; k < 3 && ok; k++) {
+            if (k) ok = expect(p, e, ' ');
+            ok = ok && scan_int(p, e, v[k]) && expect(p, e, '/') && expect(p, e, '/') && scan_int(p, e, n[k]);
+        }
+        // Sscanf targets are (&vn0, &vn1, &vn1): vn1 takes the third value, vn2 stays 0
+        vn[0] = n[0]; vn[1] = n[2]; vn[2] = 0;
+        for (int k = 0; k < 3; k++) vn[k] = vn[k] - vnOff - 1;
+    } else if (slashes == 3) {
+        has_vt = true;
+        for (int k = 0; k < 3 && ok; k++) {
+            if (k) ok = expect(p, e, ' ');
+            ok = ok && scan_int(p, e, v[k]) && expect(p, e, '/') && scan_int(p, e, vt[k]);
+        }
+    } else if (slashes == 6) {
+        has_vt = true;
+        for (int k = 0; k < 3 && ok; k++) {
+            if (k) ok = expect(p, e, ' ');
+            ok = ok && scan_int(p, e, v[k]) && expect(p, e, '/') && scan_int(p, e, vt[k]) && expect(p, e, '/') &&
+                 scan_int(p, e, vn[k]);
+        }
+        for (int k = 0; k < 3; k++) vn[k] = vn[k] - vnOff - 1;
+    } else {
+        for (int k = 0; k < 3 && ok; k++) {
+            if (k) ok = expect(p, e, ' ');
+            ok = ok && scan_int(p, e, v[k]);
+        }
+    }
+    if (!ok) return "unexpected input in face statement";   // the Sscanf error
+    for (int k = 0; k < 6; k++) uvs[k] = 0.0f;
+    if (has_vt)
+        for (int k = 0; k < 3; k++) {
+            // c.TextureVertices holds the texture vertices read SO FAR in this mesh: a forward reference panics too
+            const long idx = vt[k] - vtOff - 1;
+            if (idx < 0 || (size_t)idx >= sg.vt1 - sg.vt0) return "index out of range";   // Go: runtime panic
+            uvs[2 * k] = tv[2 * (sg.vt0 + (size_t)idx)];
+            uvs[2 * k + 1] = tv[2 * (sg.vt0 + (size_t)idx) + 1];
+        }
+    for (int k = 0; k < 3; k++) {
+        vidx[k] = (int32_t)(v[k] - vOff - 1);
+        nidx[k] = (int32_t)vn[k];
+    }
+    return "";
+}
+
 struct Parser {
     grb_obj *out;
     bool single;
     std::string dirname, err;
-    ObjMesh cur;
-    std::vector<float> tverts;                 // u, v
-    long vOff = 0, vtOff = 0, vnOff = 0;       // ObjContext offsets (obj.go:26-28)
     std::map<std::string, int> materialTex;    // c.Textures: material name -> texture source
     std::map<std::string, int> fileTex;        // textureFiles: map_Kd -> texture source
     int defaultTex = -1, currentTex = -1;
 
-    size_t nverts() const { return cur.vertices.size() / 4; }
-
-    void flush() {   // NewMesh + ObjContext.Clear (obj.go:31-40)
-        vOff += (long)nverts();
-        vtOff += (long)(tverts.size() / 2);
-        vnOff += (long)(cur.vnormals.size() / 4);
-        out->meshes.push_back(std::move(cur));
-        cur = ObjMesh();
-        tverts.clear();
-    }
-
     bool fail(const std::string &m) { err = m; return false; }
-
-    bool uv_at(long idx, float *dst) {
-        if (idx < 0 || (size_t)idx >= tverts.size() / 2) return fail("index out of range");   // Go: runtime panic
-        dst[0] = tverts[2 * idx];
-        dst[1] = tverts[2 * idx + 1];
-        return true;
-    }
-
-    // parseFace (obj.go:60-151)
-    bool face(Span line) {
-        if (count_char(line, ' ') != 3) return fail("mesh is not triangulated");
-        const int slashes = count_char(line, '/');
-        long v[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, vn[3] = {0, 0, 0};
-        const char *p = line.b + 2, *e = line.e;
-        bool ok = true, has_vt = false;
-        if (count_double_slash(line) == 3) {
-            long n[3];
-            for (int k = 0; k < 3 && ok; k++) {
-                if (k) ok = expect(p, e, ' ');
-                ok = ok && scan_int(p, e, v[k]) && expect(p, e, '/') && expect(p, e, '/') && scan_int(p, e, n[k]);
-            }
-            // Sscanf targets are (&vn0, &vn1, &vn1): vn1 takes the third value, vn2 stays 0
-            vn[0] = n[0]; vn[1] = n[2]; vn[2] = 0;
-            for (int k = 0; k < 3; k++) vn[k] = vn[k] - vnOff - 1;
-        } else if (slashes == 3) {
-            has_vt = true;
-            for (int k = 0; k < 3 && ok; k++) {
-                if (k) ok = expect(p, e, ' ');
-                ok = ok && scan_int(p, e, v[k]) && expect(p, e, '/') && scan_int(p, e, vt[k]);
-            }
-        } else if (slashes == 6) {
-            has_vt = true;
-            for (int k = 0; k < 3 && ok; k++) {
-                if (k) ok = expect(p, e, ' ');
-                ok = ok && scan_int(p, e, v[k]) && expect(p, e, '/') && scan_int(p, e, vt[k]) && expect(p, e, '/') &&
-                     scan_int(p, e, vn[k]);
-            }
-            for (int k = 0; k < 3; k++) vn[k] = vn[k] - vnOff - 1;
-        } else {
-            for (int k = 0; k < 3 && ok; k++) {
-                if (k) ok = expect(p, e, ' ');
-                ok = ok && scan_int(p, e, v[k]);
-            }
-        }
-        if (!ok) return fail("unexpected input in face statement");   // the Sscanf error
-        float uv[6] = {0, 0, 0, 0, 0, 0};
-        if (has_vt)
-            for (int k = 0; k < 3; k++)
-                if (!uv_at(vt[k] - vtOff - 1, uv + 2 * k)) return false;
-        for (int k = 0; k < 3; k++) {
-            cur.vidx.push_back((int32_t)(v[k] - vOff - 1));
-            cur.nidx.push_back((int32_t)vn[k]);
-        }
-        cur.uvs.insert(cur.uvs.end(), uv, uv + 6);
-        cur.tex.push_back(currentTex);
-        return true;
-    }
 
     int source(const std::string &path) {
         out->sources.push_back({path});
@@ -321,34 +349,100 @@ struct Parser {
         std::string text;
         if (!read_file(filename, text, err)) return false;
         dirname = dir_of(filename);
+
+        // ---- pass 1 (serial): classify, run the order-dependent statements
+        std::vector<FloatLine> vLines, vtLines, vnLines;
+        std::vector<FaceLine> fLines;
+        std::vector<Segment> segs;
+        Segment cur{0, 0, 0, 0, 0, 0, 0, 0};
+        ErrorSlot first;
+        size_t ordinal = 0;
         const char *p = text.data(), *end = p + text.size();
-        float f[3];
         while (p < end) {
             const char *nl = (const char *)std::memchr(p, '\n', (size_t)(end - p));
             Span line = trim({p, nl ? nl : end});
             p = nl ? nl + 1 : end;
             if (line.size() == 0) continue;
+            ordinal++;
             if (line.b[0] == 'v' && line.has_prefix("v ")) {
-                if (!scan_floats(line, 2, f, 3)) return fail("unexpected EOF");
-                cur.vertices.insert(cur.vertices.end(), {f[0], f[1], f[2], 1.0f});
+                vLines.push_back({line, ordinal});
             } else if (line.b[0] == 'f' && line.has_prefix("f ")) {
-                if (!face(line)) return false;
+                fLines.push_back({line, ordinal, currentTex, (int32_t)segs.size()});
             } else if (line.has_prefix("vt ")) {
-                if (!scan_floats(line, 3, f, 2)) return fail("unexpected EOF");
-                tverts.insert(tverts.end(), {f[0], f[1]});
+                vtLines.push_back({line, ordinal});
             } else if (line.has_prefix("vn ")) {
-                if (!scan_floats(line, 3, f, 3)) return fail("unexpected EOF");
-                cur.vnormals.insert(cur.vnormals.end(), {f[0], f[1], f[2], 1.0f});   // w = 1 (obj.go:57)
+                vnLines.push_back({line, ordinal});
             } else if (line.has_prefix("mtllib ")) {
-                if (!mtllib(line.str(7))) return false;
+                if (!mtllib(line.str(7))) {   // the reference stops here; earlier lines may still fail first
+                    first.report(ordinal, err);
+                    break;
+                }
             } else if (line.has_prefix("o ")) {
-                if (nverts() != 0 && !single) flush();
+                if (vLines.size() != cur.v0 && !single) {   // NewMesh + ObjContext.Clear (obj.go:31-40, 257-262)
+                    cur.v1 = vLines.size(); cur.vt1 = vtLines.size(); cur.vn1 = vnLines.size(); cur.f1 = fLines.size();
+                    segs.push_back(cur);
+                    cur = {cur.v1, cur.vt1, cur.vn1, cur.f1, 0, 0, 0, 0};
+                }
             } else if (line.has_prefix("usemtl ")) {
                 auto it = materialTex.find(line.str(7));
                 currentTex = it == materialTex.end() ? -1 : it->second;   // unknown name -> nil texture
             }
         }
-        if (nverts() != 0) flush();
+        cur.v1 = vLines.size(); cur.vt1 = vtLines.size(); cur.vn1 = vnLines.size(); cur.f1 = fLines.size();
+        const bool tail = cur.v1 != cur.v0;     // obj.go:296-299: the last mesh needs vertices
+        if (tail) segs.push_back(cur);
+
+        // ---- pass 2 (parallel): the floats
+        std::vector<float> V(4 * vLines.size()), VN(4 * vnLines.size()), VT(2 * vtLines.size());
+        auto floats = [&](const std::vector<FloatLine> &lines, size_t prefix, int n, int stride, float w, std::vector<float> &dst) {
+            parallel_for(lines.size(), [&, prefix, n, stride, w](size_t b, size_t e) {
+                float f[3];
+                for (size_t i = b; i < e; i++) {
+                    if (!scan_floats(lines[i].line, prefix, f, n)) { first.report(lines[i].ordinal, "unexpected EOF"); continue; }
+                    for (int k = 0; k < n; k++) dst[stride * i + k] = f[k];
+                    if (stride == 4) dst[4 * i + 3] = w;   // Vec4{x, y, z, 1} (obj.go:45, 57)
+                }
+            });
+        };
+        floats(vLines, 2, 3, 4, 1.0f, V);
+        floats(vtLines, 3, 2, 2, 0.0f, VT);
+        floats(vnLines, 3, 3, 4, 1.0f, VN);
+
+        // ---- pass 3 (parallel): the faces (they read the texture vertices parsed above)
+        const size_t nf = fLines.size();
+        std::vector<int32_t> VI(3 * nf), NI(3 * nf);
+        std::vector<float> UV(6 * nf);
+        parallel_for(nf, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; i++) {
+                const FaceLine &fl = fLines[i];
+                // (a face after the last mesh with vertices lands in no mesh, but is parsed — and can fail — all the same)
+                Segment sg = (size_t)fl.seg < segs.size() ? segs[fl.seg] : cur;
+                // only the texture vertices that precede the face in the file exist yet (obj.go:107-109)
+                size_t lo = sg.vt0, hi = sg.vt1;
+                while (lo < hi) {   // number of vt lines of this mesh before this face
+                    const size_t mid = (lo + hi) / 2;
+                    if (vtLines[mid].ordinal < fl.ordinal) lo = mid + 1; else hi = mid;
+                }
+                sg.vt1 = lo;
+                const std::string m = parse_face(fl.line, sg, VT.data(), &VI[3 * i], &NI[3 * i], &UV[6 * i]);
+                if (!m.empty()) first.report(fl.ordinal, m);
+            }
+        });
+        if (first.ordinal != SIZE_MAX) return fail(first.msg);
+
+        // ---- meshes
+        for (size_t k = 0; k < segs.size(); k++) {
+            const Segment &sg = segs[k];
+            ObjMesh m;
+            m.vertices.assign(V.begin() + 4 * sg.v0, V.begin() + 4 * sg.v1);
+            m.vnormals.assign(VN.begin() + 4 * sg.vn0, VN.begin() + 4 * sg.vn1);
+            m.vidx.assign(VI.begin() + 3 * sg.f0, VI.begin() + 3 * sg.f1);
+            m.nidx.assign(NI.begin() + 3 * sg.f0, NI.begin() + 3 * sg.f1);
+            m.uvs.assign(UV.begin() + 6 * sg.f0, UV.begin() + 6 * sg.f1);
+            m.tex.resize(sg.f1 - sg.f0);
+            for (size_t i = sg.f0; i < sg.f1; i++) m.tex[i - sg.f0] = fLines[i].tex;
+            out->meshes.push_back(std::move(m));
+        }
         if (out->meshes.empty()) return fail("obj file does not have any vertices data");
         return true;
     }

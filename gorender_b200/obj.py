@@ -135,6 +135,15 @@ class _ObjContext:
 _NO_VT = np.iinfo(np.int64).min
 
 
+def _vt_indices(c: _ObjContext, idx):
+    """obj.go:107-109, 131-133 index c.TextureVertices while parsing the face: only the texture vertices read so
+    far exist, and an index outside them is a Go runtime panic."""
+    n = len(c.TextureVertices) // 2
+    if any(i < 0 or i >= n for i in idx):
+        raise IndexError("texture vertex index out of range")
+    return idx
+
+
 def _parseFace(c: _ObjContext, line: str) -> None:
     """obj.go:60-151."""
     if line.count(" ") != 3:
@@ -152,12 +161,12 @@ def _parseFace(c: _ObjContext, line: str) -> None:
     elif line.count("/") == 3:
         p = [t.split("/") for t in toks]
         c.face_v += [int(q[0]) - vo - 1 for q in p]
-        c.face_vt += [int(q[1]) - to - 1 for q in p]
+        c.face_vt += _vt_indices(c, [int(q[1]) - to - 1 for q in p])
         c.face_vn += [0, 0, 0]
     elif line.count("/") == 6:
         p = [t.split("/") for t in toks]
         c.face_v += [int(q[0]) - vo - 1 for q in p]
-        c.face_vt += [int(q[1]) - to - 1 for q in p]
+        c.face_vt += _vt_indices(c, [int(q[1]) - to - 1 for q in p])
         c.face_vn += [int(q[2]) - no - 1 for q in p]
     else:
         c.face_v += [int(t) - vo - 1 for t in toks]

@@ -168,3 +168,43 @@ def test_float_parsing_is_correctly_rounded(tmp_path):
     libc.strtof.argtypes = [C.c_char_p, C.c_void_p]
     want = np.array([libc.strtof(t.encode(), None) for t in toks], np.float32)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_forward_references_and_order(tmp_path):
+    """A face may only use the texture vertices read so far (obj.go:107-109 indexes c.TextureVertices, a slice that
+    grows line by line): a forward reference panics in the reference and must fail here too, also in the threaded
+    parser, and of several bad lines the first in file order is the one reported."""
+    p = tmp_path / "fwd.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nf 1/1 2/1 3/2\nvt 1 1\n")
+    with pytest.raises(IndexError):
+        g.LoadObjFileNative(str(p), False)
+    with pytest.raises(IndexError):
+        g.LoadObjFile(str(p), False)
+    q = tmp_path / "two_errors.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3 4\nv 1\n")
+    with pytest.raises(ValueError, match="mesh is not triangulated"):
+        g.LoadObjFileNative(str(q), False)
+    r = tmp_path / "two_errors_b.obj"
+    r.write_text("v 0 0 0\nv 1\nv 0 1 0\nf 1 2 3 4\n")
+    with pytest.raises(ValueError, match="unexpected EOF"):
+        g.LoadObjFileNative(str(r), False)
+
+
+def test_large_file_threaded_path(tmp_path):
+    """Enough lines for the threaded passes (>= 20 000 per thread): two objects, identical to the Python mirror."""
+    a, b = tmp_path / "a.obj", tmp_path / "b.obj"
+    geometry.write_obj(geometry.geodesic_sphere(48, True), str(a))      # 46 080 faces
+    geometry.write_obj(geometry.geodesic_sphere(40, False), str(b))     # 32 000 faces, `f a b c`
+    # second object's indices continue after the first's (OBJ numbering is global; obj.go:31-40 rebases them)
+    na = sum(1 for ln in open(a) if ln.startswith("v "))
+    with open(tmp_path / "both.obj", "w") as out:
+        out.write(open(a).read())
+        for ln in open(b):
+            if ln.startswith("f "):
+                i, j, k = (int(t) + na for t in ln.split()[1:])
+                out.write(f"f {i} {j} {k}\n")
+            else:
+                out.write(ln)
+    path = str(tmp_path / "both.obj")
+    for single in (False, True):
+        assert_same_meshes(g.LoadObjFile(path, single), g.LoadObjFileNative(path, single))
