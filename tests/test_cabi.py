@@ -69,3 +69,19 @@ def test_graft_entry_build():
     import __graft_entry__ as ge
 
     ge.build()
+
+
+def test_option_bits_match_header():
+    """The GRB_OPT_* / GRB_TEX_* / GRB_BOX_* values of the ctypes binding and of the oracle's header are the header's."""
+    src = open(os.path.join(ROOT, "include", "gorender_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    bits = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"\b(GRB_OPT_[A-Z_]+)\s*=\s*1u\s*<<\s*(\d+)", src)}
+    assert len(bits) == 10
+    for name, value in bits.items():
+        assert getattr(_cabi, name) == value, name
+    orc = open(os.path.join(ROOT, "oracle", "gorender_oracle.h")).read()
+    orc = re.sub(r"/\*.*?\*/", "", orc, flags=re.S)
+    obits = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"\bORC_OPT_([A-Z_]+)\s*=\s*1u\s*<<\s*(\d+)", orc)}
+    assert {("GRB_OPT_" + k): v for k, v in obits.items()} == bits     # tests feed Renderer.options() to both sides
+    assert int(re.search(r"#define GRB_ABI_VERSION (\d+)", src).group(1)) == _cabi.GRB_ABI_VERSION
+    assert int(re.search(r"#define GRB_TILE (\d+)", src).group(1)) == _cabi.GRB_TILE
