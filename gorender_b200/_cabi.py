@@ -29,7 +29,10 @@ GRB_OPT_FOG = 1 << 9
 GRB_OPT_DEFAULT = (GRB_OPT_FRUSTUM_CLIPPING | GRB_OPT_SHOW_FACES | GRB_OPT_BACKFACE_CULLING |
                    GRB_OPT_LIGHTING | GRB_OPT_SHOW_TEXTURES)
 GRB_TILE = 32
-GRB_ABI_VERSION = 2
+GRB_IPC_HANDLE_BYTES = 320
+GRB_SIGNAL_SLOTS = 64
+GRB_ABI_VERSION = 3
+GRB_PLANE_COLOR, GRB_PLANE_DEPTH = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
 c_i32_p = C.POINTER(C.c_int32)
@@ -71,7 +74,7 @@ class grb_triangle_rec(C.Structure):
 
 class grb_frame_stats(C.Structure):
     _fields_ = [("tpf", C.c_int64), ("triangles", C.c_int32), ("big_triangles", C.c_int32),
-                ("out_of_domain", C.c_int32), ("reserved", C.c_int32)]
+                ("out_of_domain", C.c_int32), ("list_fallbacks", C.c_int32)]
 
 
 # numpy mirrors of the two array-of-struct ABI types
@@ -83,7 +86,7 @@ TRIANGLE_DTYPE = np.dtype([
     ("bx0", np.int16), ("by0", np.int16), ("bx1", np.int16), ("by1", np.int16),
     ("tex", np.int32), ("order", np.uint32)])
 STATS_DTYPE = np.dtype([("tpf", np.int64), ("triangles", np.int32), ("big_triangles", np.int32),
-                        ("out_of_domain", np.int32), ("reserved", np.int32)])
+                        ("out_of_domain", np.int32), ("list_fallbacks", np.int32)])
 assert OBJECT_DTYPE.itemsize == C.sizeof(grb_object) == 132
 assert TRIANGLE_DTYPE.itemsize == C.sizeof(grb_triangle_rec) == 64
 assert STATS_DTYPE.itemsize == C.sizeof(grb_frame_stats) == 24
@@ -101,8 +104,12 @@ SIGNATURES = {
     "grb_context_set_stage_capture": (C.c_int32, [_VP, C.c_int32]),
     "grb_kernel_times": (C.c_int32, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "grb_launch_count": (C.c_int64, [_VP]),
+    "grb_context_set_workspace_limit": (C.c_int32, [_VP, C.c_uint64]),
+    "grb_context_trim": (C.c_int32, [_VP]),
     "grb_host_alloc": (_VP, [C.c_uint64]),
     "grb_host_free": (None, [_VP]),
+    "grb_host_register": (C.c_int32, [_VP, C.c_uint64]),
+    "grb_host_unregister": (C.c_int32, [_VP]),
     "grb_texture_upload": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_float, c_u8_p, _VP, c_i32_p]),
     "grb_texture_set_scale": (C.c_int32, [_VP, C.c_int32, C.c_float]),
     "grb_mesh_upload": (C.c_int32, [_VP, C.POINTER(grb_mesh_desc), c_i32_p]),
@@ -118,6 +125,12 @@ SIGNATURES = {
     "grb_framebuffer_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_VP)]),
     "grb_framebuffer_wrap": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.POINTER(_VP)]),
     "grb_framebuffer_destroy": (C.c_int32, [_VP]),
+    "grb_framebuffer_ipc_export": (C.c_int32, [_VP, _VP]),
+    "grb_framebuffer_ipc_open": (C.c_int32, [_VP, _VP, C.POINTER(_VP)]),
+    "grb_framebuffer_signal": (C.c_int32, [_VP, _VP, C.c_int32, C.c_uint32]),
+    "grb_framebuffer_wait_signals": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_uint32, C.c_int32]),
+    "grb_context_signal_timeouts": (C.c_int64, [_VP]),
+    "grb_framebuffer_read_tile_flags": (C.c_int32, [_VP, C.c_int32, _VP]),
     "grb_framebuffer_device_ptrs": (C.c_int32, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     "grb_draw_async": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int32, C.POINTER(grb_draw_params)]),
     "grb_draw": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int32, C.POINTER(grb_draw_params), _VP]),
@@ -125,10 +138,20 @@ SIGNATURES = {
     "grb_read_frames": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     "grb_read_frames_async": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     "grb_framebuffer_wait": (C.c_int32, [_VP]),
+    "grb_mirror_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, C.POINTER(_VP)]),
+    "grb_mirror_destroy": (C.c_int32, [_VP]),
+    "grb_mirror_invalidate": (C.c_int32, [_VP]),
+    "grb_mirror_update_async": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, C.c_int32]),
+    "grb_mirror_wait": (C.c_int32, [_VP]),
+    "grb_mirror_stats": (C.c_int32, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "grb_draw_present": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int32, C.POINTER(grb_draw_params),
+                                     _VP, C.c_int32, _VP, C.c_int32, _VP]),
+    "grb_graph_replays": (C.c_int64, [_VP]),
     "grb_matrix_multiply_vec4_batch": (C.c_int32, [_VP, c_float_p, _VP, C.c_int64]),
     "grb_matrix_multiply_vec4_batch_device": (C.c_int32, [_VP, c_float_p, _VP, C.c_int64]),
     "grb_debug_read_transformed": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int64, C.POINTER(C.c_int64)]),
     "grb_debug_read_triangles": (C.c_int32, [_VP, C.c_int32, _VP, _VP, C.c_int64, C.POINTER(C.c_int64)]),
+    "grb_debug_set_overflow_cap": (C.c_int32, [_VP, C.c_uint32]),
     "grb_debug_read_visibility": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32]),
 }
 

@@ -43,6 +43,13 @@ template <typename T> struct DevBuf {
 };
 
 constexpr int kStagingRing = 4;
+constexpr int kFlagStride = 32;   // words between two hand-off flags: one 128-byte line each
+
+struct IpcHandle {       // what grb_framebuffer_ipc_export writes into the caller's GRB_IPC_HANDLE_BYTES
+    cudaIpcMemHandle_t color, depth, flags, busy;
+    int32_t width, height, frames, magic;
+};
+static_assert(sizeof(IpcHandle) <= GRB_IPC_HANDLE_BYTES, "IPC handle does not fit");
 
 }  // namespace
 
@@ -52,11 +59,30 @@ struct grb_framebuffer {
     uchar4 *color;
     float *depth;
     bool owned;
+    // [frames][nTiles] one byte per device tile, written by the raster kernel: the tile holds something
+    // other than the cleared background (1 until a frame has been drawn: contents unknown)
+    uint8_t *tileBusy = nullptr;
+    // hand-off flags (GRB_SIGNAL_SLOTS words, kFlagStride apart) of a framebuffer shared across processes
+    uint32_t *flags = nullptr;
+    bool ipcOpened = false;       // colour / depth / flags are another process's memory (cudaIpcOpenMemHandle)
     // read-backs run on the context's copy stream so that the D2H of one
     // framebuffer overlaps the rendering of another
     cudaEvent_t drawDone = nullptr, readDone = nullptr;
     bool pendingRead = false;
 };
+
+struct grb_mirror {
+    grb_context *ctx;
+    int32_t width, height, frames, plane;
+    void *devPtr;                 // device-visible address of the pinned host plane
+    uint8_t *dirty = nullptr;     // [frames][nTiles] device flags: the HOST tile is not the cleared background
+    unsigned long long *tilesWritten = nullptr;   // device counter
+    int64_t tilesFull = 0;        // tiles full copies would have moved
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+};
+
+struct GraphEntry;
 
 struct grb_context {
     int device = 0;
@@ -86,7 +112,21 @@ struct grb_context {
     int stagingNext = 0;
     DevBuf<FrameObj> dFrameObjs;
 
+    // staging + read-back of the one-call Draw (grb_draw_present): synchronous, so one buffer each
+    FrameObj *hGraphObjs = nullptr;
+    size_t hGraphObjsCap = 0;
+    FrameCounters *hCounters = nullptr;
+    size_t hCountersCap = 0;
+    std::vector<GraphEntry *> graphs;   // cached CUDA graphs of one-frame draws (most recent first)
+    int64_t graphReplays = 0, graphCaptures = 0;
+
     // workspace
+    uint64_t workspaceLimit = 0;        // bytes; 0 = a quarter of the device's memory
+    uint64_t deviceMemory = 0;
+    uint32_t overflowCap = 0;           // per frame
+    uint32_t overflowCapForced = 0;     // grb_debug_set_overflow_cap (tests of the fallback path)
+    uint32_t *dTimeouts = nullptr;      // device counter of signal waits that gave up
+    bool descDirty = false;             // a draw's setup ran but its raster did not: descCount is not all zero
     DevBuf<float4> tv;
     DevBuf<PackedRec> rec;
     DevBuf<TriUV> uv;
@@ -131,6 +171,8 @@ int32_t fail(const grb_context *ctx, int32_t code, const std::string &msg) {
             return fail(ctx, code__, std::string(#call) + ": " + cudaGetErrorString(e__));              \
         }                                                                                               \
     } while (0)
+
+void free_graph(GraphEntry *g);
 
 // Grow a device buffer to at least n elements.  Old contents are dropped;
 // zero-filled when `zero`.  Synchronises the stream before freeing.
@@ -259,8 +301,27 @@ int32_t set_device(const grb_context *ctx) {
     return GRB_OK;
 }
 
-int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, const grb_object *objects,
-                  int32_t nobj, const grb_draw_params *prm) {
+// Everything one draw call needs, worked out on the host before anything is queued.  Plain data, zero
+// filled before use: two jobs that compare equal byte for byte queue exactly the same work, which is what
+// the CUDA-graph cache of grb_draw_present keys on.
+struct DrawJob {
+    DrawArgs a;              // pointers of the batch's first frame; enqueue_draw offsets them per launch
+    int32_t nframes, nobj, chunk, nTiles;
+    int32_t anyPlain, anyClip, overlayKeys, ring;
+    size_t nfo, npix;
+    FrameObj *hfo;           // pinned staging of the per-(frame, object) matrices, filled
+};
+
+uint64_t workspace_limit(const grb_context *ctx) {
+    if (ctx->workspaceLimit) return ctx->workspaceLimit;
+    return ctx->deviceMemory ? ctx->deviceMemory / 4 : (uint64_t)32 << 30;
+}
+
+// Host part of a draw: validation, BoxVisibility per (frame, object) (renderer.go:268-275), the matrices into
+// pinned staging, workspace sizing.  `oneCall`: the synchronous one-call path (its own staging buffer).
+int32_t prepare_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, const grb_object *objects,
+                     int32_t nobj, const grb_draw_params *prm, bool oneCall, DrawJob &job) {
+    std::memset(&job, 0, sizeof job);
     if (!ctx || !fb || !prm) return fail(ctx, GRB_ERR_INVALID, "null argument");
     if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
     if (nframes <= 0 || frame0 < 0 || frame0 + nframes > fb->frames)
@@ -295,27 +356,44 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
 
     // ---- per (frame, object): matrices + BoxVisibility (renderer.go:268-275)
     const size_t nfo = (size_t)nframes * std::max(nobj, 1);
-    const int ring = ctx->stagingNext;
-    ctx->stagingNext = (ring + 1) % kStagingRing;
-    if (ctx->hFrameObjsCap[ring] < nfo) {
-        if (ctx->hFrameObjs[ring]) {
-            CK(ctx, cudaEventSynchronize(ctx->stagingDone[ring]));
-            CK(ctx, cudaFreeHost(ctx->hFrameObjs[ring]));
-            ctx->hFrameObjs[ring] = nullptr;
+    FrameObj *hfo;
+    if (oneCall) {
+        // the previous one-call draw has completed (it synchronises): the buffer is free
+        if (ctx->hGraphObjsCap < nfo) {
+            if (ctx->hGraphObjs) CK(ctx, cudaFreeHost(ctx->hGraphObjs));
+            ctx->hGraphObjs = nullptr;
+            ctx->hGraphObjsCap = 0;
+            for (GraphEntry *g : ctx->graphs) free_graph(g);   // they copy from the old buffer
+            ctx->graphs.clear();
+            CK(ctx, cudaHostAlloc((void **)&ctx->hGraphObjs, (nfo + 16) * sizeof(FrameObj), cudaHostAllocDefault));
+            ctx->hGraphObjsCap = nfo + 16;
         }
-        CK(ctx, cudaHostAlloc((void **)&ctx->hFrameObjs[ring], nfo * sizeof(FrameObj), cudaHostAllocDefault));
-        ctx->hFrameObjsCap[ring] = nfo;
+        hfo = ctx->hGraphObjs;
+        job.ring = -1;
     } else {
-        CK(ctx, cudaEventSynchronize(ctx->stagingDone[ring]));
+        const int ring = ctx->stagingNext;
+        ctx->stagingNext = (ring + 1) % kStagingRing;
+        if (ctx->hFrameObjsCap[ring] < nfo) {
+            if (ctx->hFrameObjs[ring]) {
+                CK(ctx, cudaEventSynchronize(ctx->stagingDone[ring]));
+                CK(ctx, cudaFreeHost(ctx->hFrameObjs[ring]));
+                ctx->hFrameObjs[ring] = nullptr;
+            }
+            CK(ctx, cudaHostAlloc((void **)&ctx->hFrameObjs[ring], nfo * sizeof(FrameObj), cudaHostAllocDefault));
+            ctx->hFrameObjsCap[ring] = nfo;
+        } else {
+            CK(ctx, cudaEventSynchronize(ctx->stagingDone[ring]));
+        }
+        hfo = ctx->hFrameObjs[ring];
+        job.ring = ring;
     }
-    FrameObj *hfo = ctx->hFrameObjs[ring];
 
     const bool optClip = prm->options & GRB_OPT_FRUSTUM_CLIPPING;
     bool anyPlain = false, anyClip = false;
-    uint64_t recNeed = 1;
+    uint64_t recNeed = 1, facesMax = 1;
     ctx->lastVisibility.assign((size_t)nframes * nobj, GRB_BOX_OUTSIDE);
     for (int32_t f = 0; f < nframes; f++) {
-        uint64_t need = 0;  // record slots of this frame: static per-warp segments (setup.cu)
+        uint64_t need = 0, faces = 0;  // record slots of this frame: static per-warp segments (setup.cu)
         for (int32_t i = 0; i < nobj; i++) {
             const grb_object &src = objects[(size_t)f * nobj + i];
             FrameObj &dst = hfo[(size_t)f * nobj + i];
@@ -330,52 +408,67 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
             const int vis = box_visibility(corners, prm->z_near, prm->z_far);
             dst.visibility = vis;
             dst.slotBase = (uint32_t)need;
+            dst.pad[0] = dst.pad[1] = 0;
             ctx->lastVisibility[(size_t)f * nobj + i] = vis;
             if (vis == GRB_BOX_OUTSIDE) continue;
             const bool clips = optClip && vis != GRB_BOX_INSIDE;
             (clips ? anyClip : anyPlain) = true;
             const uint64_t blocks = (mh.dev.nf + kFaceBlock - 1) / kFaceBlock;
             need += blocks * kWarpsPerFaceBlock * (clips ? kWarpSlotsClip : kWarpSlots);
+            faces += (uint64_t)mh.dev.nf;
         }
         recNeed = std::max(recNeed, need);
+        facesMax = std::max(facesMax, faces);
     }
-    if (recNeed * kMaxBinsPerTri > UINT32_MAX) return fail(ctx, GRB_ERR_INVALID, "too many triangles per frame");
+    if (recNeed >= UINT32_MAX) return fail(ctx, GRB_ERR_INVALID, "too many triangles per frame");
 
-    // ---- workspace
+    // ---- workspace.  Records have static slots (exact worst case); tile lists hold kDescCap descriptors in
+    // place and share a bounded overflow pool per frame; what fits nowhere goes to the frame-wide list (setup.cu).
     const int nTiles = ntx * nty;
     const uint32_t recCap = std::max<uint32_t>(ctx->recCap, (uint32_t)recNeed);
-    const size_t F = (size_t)nframes;
-    // a larger per-frame stride invalidates nothing that is live across draws except the zeroed tile counters
-    if (int32_t r = ensure(ctx, ctx->dFrameObjs, nfo, false)) return r;
-    if (ctx->stageCapture)
-        if (int32_t r = ensure(ctx, ctx->tv, F * std::max(ctx->totalVerts, 1), false)) return r;
-    if (int32_t r = ensure(ctx, ctx->rec, F * recCap, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->uv, F * recCap, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->bigList, F * recCap, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->overflow, F * recCap * kMaxBinsPerTri, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->desc, F * nTiles * kDescCap, false)) return r;
-    if (ctx->stageCapture)
-        if (int32_t r = ensure(ctx, ctx->warpCount, F * std::max(ctx->nFaceBlocks, 1) * kWarpsPerFaceBlock, false)) return r;
-    if (int32_t r = ensure(ctx, ctx->counters, F, false)) return r;
+    const uint64_t ovWorst = (uint64_t)recCap * kMaxBinsPerTri;
+    const uint32_t ovCap = ctx->overflowCapForced
+                               ? ctx->overflowCapForced
+                               : std::max<uint32_t>(ctx->overflowCap, (uint32_t)std::min<uint64_t>(ovWorst, std::max<uint64_t>(8192, 2 * facesMax)));
     const bool overlayKeys = (prm->options & kOptOverlayKeys) != 0;
     const size_t npix = (size_t)fb->width * fb->height;
+    const size_t nWarps = (size_t)std::max(ctx->nFaceBlocks, 1) * kWarpsPerFaceBlock;
+    // a batch whose workspace would not fit the limit is rendered in several launches of `chunk` frames
+    uint64_t perFrame = (uint64_t)recCap * (sizeof(PackedRec) + sizeof(TriUV) + 4) + (uint64_t)ovCap * sizeof(OverflowDesc) +
+                        (uint64_t)nTiles * (kDescCap * sizeof(TileDesc) + 4);
+    if (overlayKeys) perFrame += npix * 8;
+    size_t chunk = (size_t)std::min<uint64_t>((uint64_t)nframes, std::max<uint64_t>(1, workspace_limit(ctx) / perFrame));
+    chunk = std::min<size_t>(chunk, 32768);   // grid.y / grid.z limit of the launches
+    if (ctx->stageCapture) {
+        if (nframes > 32768) return fail(ctx, GRB_ERR_INVALID, "stage capture draws at most 32768 frames per call");
+        chunk = (size_t)nframes;              // the stage read-backs address the whole batch
+    }
+    const size_t F = (size_t)nframes;
+    if (int32_t r = ensure(ctx, ctx->dFrameObjs, nfo, false)) return r;
+    if (ctx->stageCapture)
+        if (int32_t r = ensure(ctx, ctx->tv, chunk * std::max(ctx->totalVerts, 1), false)) return r;
+    if (int32_t r = ensure(ctx, ctx->rec, chunk * recCap, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->uv, chunk * recCap, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->bigList, chunk * recCap, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->overflow, chunk * ovCap, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->desc, chunk * nTiles * kDescCap, false)) return r;
+    if (ctx->stageCapture)
+        if (int32_t r = ensure(ctx, ctx->warpCount, chunk * nWarps, false)) return r;
+    if (int32_t r = ensure(ctx, ctx->counters, F, false)) return r;
     if (overlayKeys)
-        if (int32_t r = ensure(ctx, ctx->ovl, F * npix, false)) return r;
+        if (int32_t r = ensure(ctx, ctx->ovl, chunk * npix, false)) return r;
     ctx->recCap = recCap;
-    // per-tile descriptor counters must be zero on entry; the raster kernel re-zeroes what it
-    // consumed, but the per-frame stride depends on nTiles (and a strip draw leaves the other
-    // rows' tiles untouched, at zero), so clear only when the geometry changes
-    if (ctx->descCount.cap < F * nTiles || ctx->lastNTiles != nTiles) {
-        if (int32_t r = ensure(ctx, ctx->descCount, F * nTiles, false)) return r;
+    if (!ctx->overflowCapForced) ctx->overflowCap = ovCap;
+    // per-tile descriptor counters must be zero on entry.  The raster kernel re-zeroes what it consumed, but the
+    // per-frame stride depends on nTiles (a strip draw leaves the other rows' tiles untouched, at zero), so they
+    // are cleared when the geometry changes — and after a draw whose setup ran but whose raster did not
+    if (ctx->descCount.cap < chunk * nTiles || ctx->lastNTiles != nTiles || ctx->descDirty) {
+        if (int32_t r = ensure(ctx, ctx->descCount, chunk * nTiles, false)) return r;
         CK(ctx, cudaMemsetAsync(ctx->descCount.p, 0, ctx->descCount.cap * sizeof(uint32_t), ctx->stream));
+        ctx->descDirty = false;
     }
 
-    CK(ctx, cudaMemcpyAsync(ctx->dFrameObjs.p, hfo, nfo * sizeof(FrameObj), cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx, cudaEventRecord(ctx->stagingDone[ring], ctx->stream));
-    CK(ctx, cudaMemsetAsync(ctx->counters.p, 0, F * sizeof(FrameCounters), ctx->stream));
-    if (overlayKeys) CK(ctx, cudaMemsetAsync(ctx->ovl.p, 0, F * npix * sizeof(unsigned long long), ctx->stream));
-
-    DrawArgs a{};
+    DrawArgs &a = job.a;
     a.meshes = ctx->dMeshes.p;
     a.textures = ctx->dTextures.p;
     a.ntex = (int32_t)ctx->textures.size();
@@ -394,6 +487,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.descCount = ctx->descCount.p;
     a.desc = ctx->desc.p;
     a.overflow = ctx->overflow.p;
+    a.overflowCap = ovCap;
     a.descCap = kDescCap;
     a.bigList = ctx->bigList.p;
     a.counters = ctx->counters.p;
@@ -402,8 +496,9 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.fogStart = prm->fog_start;
     a.fogEnd = prm->fog_end;
     a.fogColor = make_uchar4(prm->fog_color[0], prm->fog_color[1], prm->fog_color[2], prm->fog_color[3]);
-    a.color = fb->color + (size_t)frame0 * fb->width * fb->height;
-    a.depth = fb->depth + (size_t)frame0 * fb->width * fb->height;
+    a.color = fb->color + (size_t)frame0 * npix;
+    a.depth = fb->depth + (size_t)frame0 * npix;
+    a.tileBusy = fb->tileBusy ? fb->tileBusy + (size_t)frame0 * nTiles : nullptr;
     a.width = fb->width;
     a.height = fb->height;
     a.ntx = ntx;
@@ -418,6 +513,10 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     a.zNear = prm->z_near;
     a.zFar = prm->z_far;
     a.screenNoZ = prm->screen[2] == 0.0f && prm->screen[6] == 0.0f;
+    // block-level rejection (setup.cu) needs a NewScreenMatrix-shaped viewport (x from x/w, y from y/w only); it pays
+    // when a strip is drawn or when some object reaches outside the frustum
+    a.rejectBlocks = a.screenNoZ && prm->screen[1] == 0.0f && prm->screen[4] == 0.0f && !overlayKeys &&
+                     (rowBegin != 0 || rowEnd != nty || anyClip);
     if (prm->ref_tiles == 1) {
         a.ref.ntx = a.ref.nty = 1;
         a.ref.tw = fb->width;
@@ -446,42 +545,16 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
             }
         }
     }
-
-    const bool anyVisible = anyPlain || anyClip;
-    cudaStream_t s = ctx->stream;
-    if (fb->pendingRead) {  // do not overwrite frames a read-back is still copying
-        CK(ctx, cudaStreamWaitEvent(s, fb->readDone, 0));
-        fb->pendingRead = false;
-    }
-    const bool tm = ctx->timing;
-    if (tm) CK(ctx, cudaEventRecord(ctx->tev[0], s));
-    // K1 only feeds the stage read-back (grb_debug_read_transformed); K2 transforms on its own
-    if (anyVisible && ctx->stageCapture) launch_transform(a, nframes, s);
-    if (tm) CK(ctx, cudaEventRecord(ctx->tev[1], s));
-    if (anyVisible) launch_setup(a, nframes, anyPlain, anyClip, s);
-    if (tm) CK(ctx, cudaEventRecord(ctx->tev[2], s));
-    // (slots 2 and 3 of the timing array were the separate bin-scan / bin-fill kernels; binning
-    // now happens inside the setup kernel)
-    if (tm) CK(ctx, cudaEventRecord(ctx->tev[3], s));
-    if (tm) CK(ctx, cudaEventRecord(ctx->tev[4], s));
-    launch_raster(a, nframes, s);
-    if (tm) CK(ctx, cudaEventRecord(ctx->tev[5], s));
-    CK(ctx, cudaGetLastError());
-    CK(ctx, cudaEventRecord(fb->drawDone, s));
-
-    int launches = 1;  // raster
-    if (anyVisible) launches += (ctx->stageCapture ? 1 : 0) + (anyPlain ? 1 : 0) + (anyClip ? 1 : 0);
-    ctx->totalLaunches += launches;
-
-    if (tm) {
-        CK(ctx, cudaEventSynchronize(ctx->tev[5]));
-        for (int k = 0; k < 5; k++) {
-            float ms = 0;
-            CK(ctx, cudaEventElapsedTime(&ms, ctx->tev[k], ctx->tev[k + 1]));
-            ctx->accMs[k] += ms;
-        }
-        ctx->accLaunches += launches;
-    }
+    job.nframes = nframes;
+    job.nobj = nobj;
+    job.chunk = (int32_t)chunk;
+    job.nTiles = nTiles;
+    job.anyPlain = anyPlain;
+    job.anyClip = anyClip;
+    job.overlayKeys = overlayKeys;
+    job.nfo = nfo;
+    job.npix = npix;
+    job.hfo = hfo;
 
     ctx->lastFrames = nframes;
     ctx->lastNobj = nobj;
@@ -489,6 +562,142 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
     ctx->lastOptions = prm->options;
     return GRB_OK;
 }
+
+int launches_of(const grb_context *ctx, const DrawJob &job) {
+    int per = 1;  // raster
+    if (job.anyPlain || job.anyClip) per += (ctx->stageCapture ? 1 : 0) + (job.anyPlain ? 1 : 0) + (job.anyClip ? 1 : 0);
+    return per * ((job.nframes + job.chunk - 1) / job.chunk);
+}
+
+// Device part: queue the matrix upload, the counter reset and the kernels of every launch of the batch on the
+// render stream.  `capture`: the stream is being captured into a CUDA graph (no event work, no timing).
+int32_t enqueue_draw(grb_context *ctx, const DrawJob &job, bool capture) {
+    cudaStream_t s = ctx->stream;
+    const size_t F = (size_t)job.nframes;
+    CK(ctx, cudaMemcpyAsync(ctx->dFrameObjs.p, job.hfo, job.nfo * sizeof(FrameObj), cudaMemcpyHostToDevice, s));
+    if (job.ring >= 0 && !capture) CK(ctx, cudaEventRecord(ctx->stagingDone[job.ring], s));
+    CK(ctx, cudaMemsetAsync(ctx->counters.p, 0, F * sizeof(FrameCounters), s));
+    const bool anyVisible = job.anyPlain || job.anyClip;
+    const bool tm = ctx->timing && !capture;
+    ctx->descDirty = true;
+    for (size_t c0 = 0; c0 < F; c0 += (size_t)job.chunk) {
+        const int nf = (int)std::min<size_t>((size_t)job.chunk, F - c0);
+        DrawArgs a = job.a;
+        a.frameObjs += c0 * (size_t)job.nobj;
+        a.counters += c0;
+        a.color += c0 * job.npix;
+        a.depth += c0 * job.npix;
+        if (a.tileBusy) a.tileBusy += c0 * (size_t)job.nTiles;
+        if (job.overlayKeys) CK(ctx, cudaMemsetAsync(ctx->ovl.p, 0, (size_t)nf * job.npix * sizeof(unsigned long long), s));
+        if (tm) CK(ctx, cudaEventRecord(ctx->tev[0], s));
+        // K1 only feeds the stage read-back (grb_debug_read_transformed); K2 transforms on its own
+        if (anyVisible && ctx->stageCapture) launch_transform(a, nf, s);
+        if (tm) CK(ctx, cudaEventRecord(ctx->tev[1], s));
+        if (anyVisible) launch_setup(a, nf, job.anyPlain, job.anyClip, s);
+        if (tm) CK(ctx, cudaEventRecord(ctx->tev[2], s));
+        // (slots 2 and 3 of the timing array were the separate bin-scan / bin-fill kernels; binning
+        // now happens inside the setup kernel)
+        if (tm) CK(ctx, cudaEventRecord(ctx->tev[3], s));
+        if (tm) CK(ctx, cudaEventRecord(ctx->tev[4], s));
+        launch_raster(a, nf, s);
+        if (tm) CK(ctx, cudaEventRecord(ctx->tev[5], s));
+        CK(ctx, cudaGetLastError());
+        if (tm) {
+            CK(ctx, cudaEventSynchronize(ctx->tev[5]));
+            for (int k = 0; k < 5; k++) {
+                float ms = 0;
+                CK(ctx, cudaEventElapsedTime(&ms, ctx->tev[k], ctx->tev[k + 1]));
+                ctx->accMs[k] += ms;
+            }
+        }
+    }
+    ctx->descDirty = false;   // every setup launch was followed by its raster launch
+    if (tm) ctx->accLaunches += launches_of(ctx, job);
+    return GRB_OK;
+}
+
+int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, const grb_object *objects,
+                  int32_t nobj, const grb_draw_params *prm) {
+    DrawJob job;
+    if (int32_t r = prepare_draw(ctx, fb, frame0, nframes, objects, nobj, prm, false, job)) return r;
+    if (fb->pendingRead) {  // do not overwrite frames a read-back is still copying
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, fb->readDone, 0));
+        fb->pendingRead = false;
+    }
+    if (int32_t r = enqueue_draw(ctx, job, false)) return r;
+    CK(ctx, cudaEventRecord(fb->drawDone, ctx->stream));
+    ctx->totalLaunches += launches_of(ctx, job);
+    return GRB_OK;
+}
+
+// ---- host mirrors (present.cu)
+
+int32_t mirror_args(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, grb_mirror *color,
+                    int32_t cf0, grb_mirror *depth, int32_t df0, MirrorArgs &m) {
+    std::memset(&m, 0, sizeof m);
+    if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
+    if (nframes <= 0 || frame0 < 0 || frame0 + nframes > fb->frames)
+        return fail(ctx, GRB_ERR_INVALID, "frame range outside the framebuffer");
+    const int ntx = (fb->width + kTile - 1) / kTile, nty = (fb->height + kTile - 1) / kTile;
+    const size_t nTiles = (size_t)ntx * nty, npix = (size_t)fb->width * fb->height;
+    struct { grb_mirror *mr; int32_t f0; int32_t plane; const char *what; } side[2] = {
+        {color, cf0, GRB_PLANE_COLOR, "colour"}, {depth, df0, GRB_PLANE_DEPTH, "depth"}};
+    for (auto &sd : side) {
+        if (!sd.mr) continue;
+        if (sd.mr->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "mirror belongs to another context");
+        if (sd.mr->plane != sd.plane) return fail(ctx, GRB_ERR_INVALID, std::string("wrong plane type for the ") + sd.what + " mirror");
+        if (sd.mr->width != fb->width || sd.mr->height != fb->height)
+            return fail(ctx, GRB_ERR_INVALID, "mirror and framebuffer sizes differ");
+        if (sd.f0 < 0 || sd.f0 + nframes > sd.mr->frames) return fail(ctx, GRB_ERR_INVALID, "frame range outside the mirror");
+    }
+    m.color = fb->color + (size_t)frame0 * npix;
+    m.depth = fb->depth + (size_t)frame0 * npix;
+    m.tileBusy = fb->tileBusy ? fb->tileBusy + (size_t)frame0 * nTiles : nullptr;
+    m.full = ((fb->owned || fb->ipcOpened) && fb->tileBusy) ? 0 : 1;   // wrapped memory may have been written by its owner
+    if (color) {
+        m.hostColor = static_cast<uchar4 *>(color->devPtr) + (size_t)cf0 * npix;
+        m.dirtyColor = color->dirty + (size_t)cf0 * nTiles;
+        m.tilesWritten = color->tilesWritten;
+    }
+    if (depth) {
+        m.hostDepth = static_cast<float *>(depth->devPtr) + (size_t)df0 * npix;
+        m.dirtyDepth = depth->dirty + (size_t)df0 * nTiles;
+        if (!m.tilesWritten) m.tilesWritten = depth->tilesWritten;
+    }
+    m.width = fb->width;
+    m.height = fb->height;
+    m.ntx = ntx;
+    m.nty = nty;
+    return GRB_OK;
+}
+
+// ---- cached CUDA graphs of one-frame draws
+
+struct GraphKey {
+    DrawJob job;
+    MirrorArgs m;
+    int32_t hasMirror, stageCapture;
+    void *countersHost;
+};
+
+}  // namespace
+
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+};
+
+namespace {
+
+void free_graph(GraphEntry *g) {
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    delete g;
+}
+
+constexpr size_t kGraphCache = 8;
 
 }  // namespace
 
@@ -519,7 +728,16 @@ int32_t grb_context_create(int32_t device, grb_context **out) {
     }
     ctx->stream = ctx->ownStream;
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
-    if ((e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess) {
+    {
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) ctx->deviceMemory = totalB;
+        else cudaGetLastError();
+    }
+    // read-backs and host-mirror updates get the highest priority: their blocks are few and short, and should
+    // not queue behind the render kernels of the next batch for SM slots
+    int prLo = 0, prHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+    if ((e = cudaStreamCreateWithPriority(&ctx->copyStream, cudaStreamNonBlocking, prHi)) != cudaSuccess) {
         cudaStreamDestroy(ctx->ownStream);
         delete ctx;
         return fail(nullptr, GRB_ERR_CUDA, std::string("context init: ") + cudaGetErrorString(e));
@@ -548,6 +766,10 @@ int32_t grb_context_destroy(grb_context *ctx) {
         if (ctx->hFrameObjs[i]) cudaFreeHost(ctx->hFrameObjs[i]);
         if (ctx->stagingDone[i]) cudaEventDestroy(ctx->stagingDone[i]);
     }
+    for (GraphEntry *g : ctx->graphs) free_graph(g);
+    if (ctx->hGraphObjs) cudaFreeHost(ctx->hGraphObjs);
+    if (ctx->hCounters) cudaFreeHost(ctx->hCounters);
+    if (ctx->dTimeouts) cudaFree(ctx->dTimeouts);
     for (int i = 0; i < 6; i++)
         if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -594,9 +816,36 @@ int32_t grb_kernel_times(grb_context *ctx, double out_ms[5], int64_t *out_launch
 
 int64_t grb_launch_count(const grb_context *ctx) { return ctx ? ctx->totalLaunches : 0; }
 
+int32_t grb_context_set_workspace_limit(grb_context *ctx, uint64_t bytes) {
+    if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
+    ctx->workspaceLimit = bytes;
+    return GRB_OK;
+}
+
+int32_t grb_context_trim(grb_context *ctx) {
+    if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
+    if (int32_t r = set_device(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->copyStream));
+    for (GraphEntry *g : ctx->graphs) free_graph(g);   // they hold the workspace addresses
+    ctx->graphs.clear();
+    auto drop = [](auto &b) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    };
+    drop(ctx->tv); drop(ctx->rec); drop(ctx->uv); drop(ctx->warpCount); drop(ctx->descCount); drop(ctx->bigList);
+    drop(ctx->desc); drop(ctx->overflow); drop(ctx->ovl); drop(ctx->seam);
+    ctx->recCap = 0;
+    ctx->overflowCap = 0;
+    ctx->lastNTiles = 0;
+    ctx->lastFrames = 0;
+    return GRB_OK;
+}
+
 void *grb_host_alloc(uint64_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
@@ -605,6 +854,24 @@ void *grb_host_alloc(uint64_t bytes) {
 
 void grb_host_free(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+int32_t grb_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return GRB_ERR_INVALID;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return GRB_ERR_CUDA;
+    }
+    return GRB_OK;
+}
+
+int32_t grb_host_unregister(void *p) {
+    if (!p) return GRB_ERR_INVALID;
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return GRB_ERR_CUDA;
+    }
+    return GRB_OK;
 }
 
 int32_t grb_texture_upload(grb_context *ctx, int32_t type, int32_t width, int32_t height, float scale,
@@ -677,6 +944,7 @@ int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, 
     float4 *f4;
     int32_t *i32;
     float2 *f2;
+    float4 *blockLo = nullptr, *blockHi = nullptr;
     uint32_t *scratch = nullptr;   // [0..6] bbox keys + NaN bits, [7] index-check flags
     const uint32_t scratchInit[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
     uint32_t scratchHost[8];
@@ -712,6 +980,15 @@ int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, 
         }
         pa.cn[k] = const_cast<float4 *>(m.dev.cn[k]);
     }
+    {
+        const size_t nb = ((size_t)d->nf + kFaceBlock - 1) / kFaceBlock;
+        if ((r = dev_alloc(ctx, nb, &f4, m.allocs))) goto bad;
+        m.dev.blockLo = f4;
+        blockLo = f4;
+        if ((r = dev_alloc(ctx, nb, &f4, m.allocs))) goto bad;
+        m.dev.blockHi = f4;
+        blockHi = f4;
+    }
     if ((r = dev_alloc(ctx, (size_t)8, &scratch, m.allocs))) goto bad;
     pa.verts = m.dev.verts; pa.vnormals = m.dev.vnormals; pa.vidx = m.dev.vidx; pa.nidx = m.dev.nidx;
     pa.nv = d->nv; pa.nvn = d->nvn; pa.nf = d->nf;
@@ -723,8 +1000,9 @@ int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, 
         if (e == cudaSuccess) e = cudaMemcpyAsync(scratch, scratchInit, sizeof(scratchInit), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) {
             launch_mesh_prepare(pa, s);
+            launch_block_bounds(m.dev.cv, d->nf, blockLo, blockHi, s);
             if (derive) launch_bbox(m.dev.verts, d->nv, scratch, s);
-            ctx->totalLaunches += (d->nf > 0 ? 1 : 0) + (derive ? 1 : 0);
+            ctx->totalLaunches += (d->nf > 0 ? 2 : 0) + (derive ? 1 : 0);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(scratchHost, scratch, sizeof(scratchHost), cudaMemcpyDeviceToHost, s);
@@ -811,6 +1089,20 @@ int32_t grb_mesh_free(grb_context *ctx, int32_t id) {
     return GRB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// one byte per (frame, tile), 1 = contents unknown / not the cleared background
+int32_t alloc_tile_flags(grb_context *ctx, grb_framebuffer *fb) {
+    const size_t n = (size_t)((fb->width + kTile - 1) / kTile) * ((fb->height + kTile - 1) / kTile) * fb->frames;
+    CK(ctx, cudaMalloc((void **)&fb->tileBusy, n));
+    CK(ctx, cudaMemsetAsync(fb->tileBusy, 1, n, ctx->stream));
+    return GRB_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int32_t grb_framebuffer_create(grb_context *ctx, int32_t width, int32_t height, int32_t frames, grb_framebuffer **out) {
     if (!ctx || !out) return fail(ctx, GRB_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -825,6 +1117,12 @@ int32_t grb_framebuffer_create(grb_context *ctx, int32_t width, int32_t height, 
         if (fb->color) cudaFree(fb->color);
         delete fb;
         return fail(ctx, GRB_ERR_OOM, std::string("framebuffer allocation: ") + cudaGetErrorString(e));
+    }
+    if (int32_t r = alloc_tile_flags(ctx, fb)) {
+        cudaFree(fb->color);
+        cudaFree(fb->depth);
+        delete fb;
+        return r;
     }
     cudaEventCreateWithFlags(&fb->drawDone, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&fb->readDone, cudaEventDisableTiming);
@@ -842,6 +1140,10 @@ int32_t grb_framebuffer_wrap(grb_context *ctx, int32_t width, int32_t height, in
     if (int32_t r = set_device(ctx)) return r;
     grb_framebuffer *fb = new grb_framebuffer{ctx, width, height, frames, static_cast<uchar4 *>(device_color),
                                               static_cast<float *>(device_depth), false};
+    if (int32_t r = alloc_tile_flags(ctx, fb)) {
+        delete fb;
+        return r;
+    }
     cudaEventCreateWithFlags(&fb->drawDone, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&fb->readDone, cudaEventDisableTiming);
     *out = fb;
@@ -857,9 +1159,126 @@ int32_t grb_framebuffer_destroy(grb_framebuffer *fb) {
         cudaFree(fb->color);
         cudaFree(fb->depth);
     }
+    if (fb->ipcOpened) {
+        cudaIpcCloseMemHandle(fb->color);
+        cudaIpcCloseMemHandle(fb->depth);
+        cudaIpcCloseMemHandle(fb->flags);
+        cudaIpcCloseMemHandle(fb->tileBusy);
+    } else {
+        if (fb->tileBusy) cudaFree(fb->tileBusy);
+        if (fb->flags) cudaFree(fb->flags);
+    }
+    // cached graphs may hold this framebuffer's addresses
+    for (GraphEntry *g : fb->ctx->graphs) free_graph(g);
+    fb->ctx->graphs.clear();
     if (fb->drawDone) cudaEventDestroy(fb->drawDone);
     if (fb->readDone) cudaEventDestroy(fb->readDone);
     delete fb;
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_ipc_export(grb_framebuffer *fb, uint8_t handle[GRB_IPC_HANDLE_BYTES]) {
+    if (!fb || !handle) return GRB_ERR_INVALID;
+    grb_context *ctx = fb->ctx;
+    if (!fb->owned || fb->ipcOpened) return fail(ctx, GRB_ERR_INVALID, "only a framebuffer created by grb_framebuffer_create can be exported");
+    if (int32_t r = set_device(ctx)) return r;
+    if (!fb->flags) {
+        CK(ctx, cudaMalloc((void **)&fb->flags, GRB_SIGNAL_SLOTS * kFlagStride * sizeof(uint32_t)));
+        CK(ctx, cudaMemset(fb->flags, 0, GRB_SIGNAL_SLOTS * kFlagStride * sizeof(uint32_t)));
+    }
+    IpcHandle h;
+    std::memset(&h, 0, sizeof h);
+    CK(ctx, cudaIpcGetMemHandle(&h.color, fb->color));
+    CK(ctx, cudaIpcGetMemHandle(&h.depth, fb->depth));
+    CK(ctx, cudaIpcGetMemHandle(&h.flags, fb->flags));
+    CK(ctx, cudaIpcGetMemHandle(&h.busy, fb->tileBusy));
+    h.width = fb->width; h.height = fb->height; h.frames = fb->frames; h.magic = 0x47524231;
+    std::memset(handle, 0, GRB_IPC_HANDLE_BYTES);
+    std::memcpy(handle, &h, sizeof h);
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_ipc_open(grb_context *ctx, const uint8_t handle[GRB_IPC_HANDLE_BYTES], grb_framebuffer **out) {
+    if (!ctx || !handle || !out) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    IpcHandle h;
+    std::memcpy(&h, handle, sizeof h);
+    if (h.magic != 0x47524231 || h.width <= 0 || h.height <= 0 || h.frames <= 0)
+        return fail(ctx, GRB_ERR_INVALID, "not a framebuffer handle of this library");
+    if (int32_t r = set_device(ctx)) return r;
+    void *c = nullptr, *d = nullptr, *f = nullptr, *b = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&c, h.color, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&d, h.depth, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&f, h.flags, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&b, h.busy, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (c) cudaIpcCloseMemHandle(c);
+        if (d) cudaIpcCloseMemHandle(d);
+        if (f) cudaIpcCloseMemHandle(f);
+        return fail(ctx, GRB_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e) +
+                                           " (the exporting process must be another process on the same node)");
+    }
+    grb_framebuffer *fb = new grb_framebuffer{ctx, h.width, h.height, h.frames, static_cast<uchar4 *>(c), static_cast<float *>(d), false};
+    fb->flags = static_cast<uint32_t *>(f);
+    fb->tileBusy = static_cast<uint8_t *>(b);     // the owner's per-tile flags: its host mirrors see every rank's rows
+    fb->ipcOpened = true;
+    cudaEventCreateWithFlags(&fb->drawDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&fb->readDone, cudaEventDisableTiming);
+    *out = fb;
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_signal(grb_context *ctx, grb_framebuffer *fb, int32_t slot, uint32_t value) {
+    if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
+    if (!fb->flags) return fail(ctx, GRB_ERR_STATE, "the framebuffer is not shared (grb_framebuffer_ipc_export / _open)");
+    if (slot < 0 || slot >= GRB_SIGNAL_SLOTS) return fail(ctx, GRB_ERR_INVALID, "signal slot out of range");
+    if (int32_t r = set_device(ctx)) return r;
+    launch_signal(fb->flags + (size_t)slot * kFlagStride, value, ctx->stream);
+    CK(ctx, cudaGetLastError());
+    ctx->totalLaunches++;
+    return GRB_OK;
+}
+
+int32_t grb_framebuffer_wait_signals(grb_context *ctx, grb_framebuffer *fb, int32_t slot0, int32_t nslots, uint32_t value,
+                                     int32_t timeout_ms) {
+    if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
+    if (!fb->flags) return fail(ctx, GRB_ERR_STATE, "the framebuffer is not shared (grb_framebuffer_ipc_export / _open)");
+    if (slot0 < 0 || nslots < 0 || slot0 + nslots > GRB_SIGNAL_SLOTS) return fail(ctx, GRB_ERR_INVALID, "signal slots out of range");
+    if (nslots == 0) return GRB_OK;
+    if (int32_t r = set_device(ctx)) return r;
+    if (!ctx->dTimeouts) {
+        CK(ctx, cudaMalloc((void **)&ctx->dTimeouts, sizeof(uint32_t)));
+        CK(ctx, cudaMemset(ctx->dTimeouts, 0, sizeof(uint32_t)));
+    }
+    const unsigned long long ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 5000) * 1000000ull;
+    launch_wait_signals(fb->flags + (size_t)slot0 * kFlagStride, kFlagStride, nslots, value, ns, ctx->dTimeouts, ctx->stream);
+    CK(ctx, cudaGetLastError());
+    ctx->totalLaunches++;
+    return GRB_OK;
+}
+
+int64_t grb_context_signal_timeouts(grb_context *ctx) {
+    if (!ctx || !ctx->dTimeouts) return 0;
+    if (set_device(ctx)) return -1;
+    uint32_t n = 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaMemcpy(&n, ctx->dTimeouts, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (int64_t)n;
+}
+
+int32_t grb_framebuffer_read_tile_flags(grb_framebuffer *fb, int32_t frame, uint8_t *out) {
+    if (!fb || !out) return GRB_ERR_INVALID;
+    grb_context *ctx = fb->ctx;
+    if (frame < 0 || frame >= fb->frames || !fb->tileBusy) return fail(ctx, GRB_ERR_INVALID, "no such frame");
+    if (int32_t r = set_device(ctx)) return r;
+    const size_t n = (size_t)((fb->width + kTile - 1) / kTile) * ((fb->height + kTile - 1) / kTile);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(out, fb->tileBusy + (size_t)frame * n, n, cudaMemcpyDeviceToHost));
     return GRB_OK;
 }
 
@@ -888,7 +1307,7 @@ int32_t grb_frame_stats_read(grb_context *ctx, int32_t nframes, grb_frame_stats 
         stats[f].triangles = (int32_t)c[f].triCount;
         stats[f].big_triangles = (int32_t)c[f].bigCount;
         stats[f].out_of_domain = (int32_t)c[f].outOfDomain;
-        stats[f].reserved = 0;
+        stats[f].list_fallbacks = (int32_t)c[f].listFallbacks;
     }
     return GRB_OK;
 }
@@ -937,6 +1356,234 @@ int32_t grb_framebuffer_wait(grb_framebuffer *fb) {
         CK(ctx, cudaEventSynchronize(fb->readDone));
         fb->pendingRead = false;
     }
+    return GRB_OK;
+}
+
+int32_t grb_mirror_create(grb_context *ctx, int32_t width, int32_t height, int32_t frames, int32_t plane, void *host_plane,
+                          grb_mirror **out) {
+    if (!ctx || !out || !host_plane) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || frames <= 0) return fail(ctx, GRB_ERR_INVALID, "bad mirror size");
+    if (plane != GRB_PLANE_COLOR && plane != GRB_PLANE_DEPTH) return fail(ctx, GRB_ERR_INVALID, "unknown plane type");
+    if ((uintptr_t)host_plane & 15) return fail(ctx, GRB_ERR_INVALID, "mirror memory must be 16-byte aligned");
+    if (int32_t r = set_device(ctx)) return r;
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, host_plane, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, GRB_ERR_INVALID, "mirror memory must come from grb_host_alloc or be pinned with grb_host_register");
+    }
+    grb_mirror *m = new grb_mirror{ctx, width, height, frames, plane, dp};
+    const size_t n = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile) * frames;
+    cudaError_t e = cudaMalloc((void **)&m->dirty, n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->tilesWritten, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->dirty, 1, n, ctx->stream);   // host contents unknown: first update writes every tile
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->tilesWritten, 0, sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (m->dirty) cudaFree(m->dirty);
+        if (m->tilesWritten) cudaFree(m->tilesWritten);
+        delete m;
+        return fail(ctx, GRB_ERR_OOM, std::string("mirror allocation: ") + cudaGetErrorString(e));
+    }
+    *out = m;
+    return GRB_OK;
+}
+
+int32_t grb_mirror_destroy(grb_mirror *m) {
+    if (!m) return GRB_OK;
+    grb_context *ctx = m->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copyStream);
+    for (GraphEntry *g : ctx->graphs) free_graph(g);   // cached graphs may write into this mirror
+    ctx->graphs.clear();
+    cudaFree(m->dirty);
+    cudaFree(m->tilesWritten);
+    if (m->done) cudaEventDestroy(m->done);
+    delete m;
+    return GRB_OK;
+}
+
+int32_t grb_mirror_invalidate(grb_mirror *m) {
+    if (!m) return GRB_ERR_INVALID;
+    grb_context *ctx = m->ctx;
+    if (int32_t r = set_device(ctx)) return r;
+    const size_t n = (size_t)((m->width + kTile - 1) / kTile) * ((m->height + kTile - 1) / kTile) * m->frames;
+    // ordered after updates already queued on either stream
+    CK(ctx, cudaStreamSynchronize(ctx->copyStream));
+    CK(ctx, cudaMemsetAsync(m->dirty, 1, n, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GRB_OK;
+}
+
+int32_t grb_mirror_update_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, grb_mirror *color,
+                                int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0) {
+    MirrorArgs m;
+    if (int32_t r = mirror_args(ctx, fb, frame0, nframes, color, color_frame0, depth, depth_frame0, m)) return r;
+    if (!color && !depth) return GRB_OK;
+    if (int32_t r = set_device(ctx)) return r;
+    cudaStream_t cs = ctx->copyStream;
+    CK(ctx, cudaEventRecord(fb->drawDone, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(cs, fb->drawDone, 0));
+    for (int32_t f0 = 0; f0 < nframes; f0 += 32768) {   // grid.y limit
+        MirrorArgs mm = m;
+        const size_t npix = (size_t)fb->width * fb->height, nTiles = (size_t)m.ntx * m.nty;
+        const int32_t nf = std::min(nframes - f0, 32768);
+        mm.color += f0 * npix; mm.depth += f0 * npix;
+        if (mm.tileBusy) mm.tileBusy += f0 * nTiles;
+        if (mm.hostColor) { mm.hostColor += f0 * npix; mm.dirtyColor += f0 * nTiles; }
+        if (mm.hostDepth) { mm.hostDepth += f0 * npix; mm.dirtyDepth += f0 * nTiles; }
+        launch_mirror_update(mm, nf, cs);
+    }
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaEventRecord(fb->readDone, cs));
+    fb->pendingRead = true;
+    for (grb_mirror *mr : {color, depth})
+        if (mr) {
+            CK(ctx, cudaEventRecord(mr->done, cs));
+            mr->pending = true;
+            mr->tilesFull += (int64_t)m.ntx * m.nty * nframes;
+        }
+    ctx->totalLaunches += (nframes + 32767) / 32768;
+    return GRB_OK;
+}
+
+int32_t grb_mirror_wait(grb_mirror *m) {
+    if (!m) return GRB_ERR_INVALID;
+    grb_context *ctx = m->ctx;
+    if (int32_t r = set_device(ctx)) return r;
+    if (m->pending) {
+        CK(ctx, cudaEventSynchronize(m->done));
+        m->pending = false;
+    }
+    return GRB_OK;
+}
+
+int32_t grb_mirror_stats(grb_mirror *m, int64_t *tiles_written, int64_t *tiles_full) {
+    if (!m) return GRB_ERR_INVALID;
+    grb_context *ctx = m->ctx;
+    if (int32_t r = set_device(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->copyStream));
+    unsigned long long w = 0;
+    CK(ctx, cudaMemcpy(&w, m->tilesWritten, sizeof w, cudaMemcpyDeviceToHost));
+    if (tiles_written) *tiles_written = (int64_t)w;
+    if (tiles_full) *tiles_full = m->tilesFull;
+    return GRB_OK;
+}
+
+int32_t grb_draw_present(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, const grb_object *objects,
+                         int32_t nobj, const grb_draw_params *params, grb_mirror *color, int32_t color_frame0,
+                         grb_mirror *depth, int32_t depth_frame0, grb_frame_stats *stats) {
+    GraphKey key;
+    std::memset(&key, 0, sizeof key);
+    if (int32_t r = prepare_draw(ctx, fb, frame0, nframes, objects, nobj, params, true, key.job)) return r;
+    key.hasMirror = (color || depth) ? 1 : 0;
+    if (key.hasMirror)
+        if (int32_t r = mirror_args(ctx, fb, frame0, nframes, color, color_frame0, depth, depth_frame0, key.m)) return r;
+    if (nframes > 32768 && key.hasMirror) return fail(ctx, GRB_ERR_INVALID, "at most 32768 frames per grb_draw_present call");
+    if (ctx->hCountersCap < (size_t)nframes) {
+        if (ctx->hCounters) CK(ctx, cudaFreeHost(ctx->hCounters));
+        ctx->hCounters = nullptr;
+        ctx->hCountersCap = 0;
+        for (GraphEntry *g : ctx->graphs) free_graph(g);   // they copy into the old buffer
+        ctx->graphs.clear();
+        CK(ctx, cudaHostAlloc((void **)&ctx->hCounters, ((size_t)nframes + 16) * sizeof(FrameCounters), cudaHostAllocDefault));
+        ctx->hCountersCap = (size_t)nframes + 16;
+    }
+    key.countersHost = ctx->hCounters;
+    key.stageCapture = ctx->stageCapture ? 1 : 0;
+    cudaStream_t s = ctx->stream;
+    if (fb->pendingRead) {  // a read-back / mirror update of these frames on the copy stream
+        CK(ctx, cudaStreamWaitEvent(s, fb->readDone, 0));
+        fb->pendingRead = false;
+    }
+    for (grb_mirror *mr : {color, depth})
+        if (mr && mr->pending) {   // an update of the same mirror still running on the copy stream
+            CK(ctx, cudaStreamWaitEvent(s, mr->done, 0));
+            mr->pending = false;
+        }
+    auto enqueue_all = [&](bool capture) -> int32_t {
+        if (int32_t r = enqueue_draw(ctx, key.job, capture)) return r;
+        if (key.hasMirror) launch_mirror_update(key.m, nframes, s);
+        CK(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters.p, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaGetLastError());
+        return GRB_OK;
+    };
+    const int launches = launches_of(ctx, key.job) + (key.hasMirror ? 1 : 0);
+    const bool graphable = nframes == 1 && !ctx->timing;
+    if (graphable) {
+        GraphEntry *hit = nullptr;
+        for (size_t i = 0; i < ctx->graphs.size(); i++)
+            if (std::memcmp(&ctx->graphs[i]->key, &key, sizeof key) == 0) {
+                hit = ctx->graphs[i];
+                ctx->graphs.erase(ctx->graphs.begin() + i);
+                break;
+            }
+        if (!hit) {
+            cudaGraph_t graph = nullptr;
+            CK(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int32_t r = enqueue_all(true);
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            ctx->descDirty = false;   // nothing has run yet
+            if (r != GRB_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                return r;
+            }
+            if (e != cudaSuccess) return fail(ctx, GRB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            hit = new GraphEntry;
+            hit->key = key;
+            hit->launches = launches;
+            const cudaError_t ei = cudaGraphInstantiate(&hit->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) {
+                delete hit;
+                return fail(ctx, GRB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei));
+            }
+            ctx->graphCaptures++;
+        } else {
+            ctx->graphReplays++;
+        }
+        ctx->graphs.insert(ctx->graphs.begin(), hit);
+        while (ctx->graphs.size() > kGraphCache) {
+            free_graph(ctx->graphs.back());
+            ctx->graphs.pop_back();
+        }
+        ctx->descDirty = true;
+        CK(ctx, cudaGraphLaunch(hit->exec, s));
+    } else {
+        if (int32_t r = enqueue_all(false)) return r;
+    }
+    CK(ctx, cudaStreamSynchronize(s));
+    ctx->descDirty = false;
+    ctx->totalLaunches += launches;
+    for (grb_mirror *mr : {color, depth})
+        if (mr) mr->tilesFull += (int64_t)key.m.ntx * key.m.nty * nframes;
+    if (stats)
+        for (int32_t f = 0; f < nframes; f++) {
+            const FrameCounters &c = ctx->hCounters[f];
+            stats[f].tpf = (int64_t)c.tpf;
+            stats[f].triangles = (int32_t)c.triCount;
+            stats[f].big_triangles = (int32_t)c.bigCount;
+            stats[f].out_of_domain = (int32_t)c.outOfDomain;
+            stats[f].list_fallbacks = (int32_t)c.listFallbacks;
+        }
+    return GRB_OK;
+}
+
+int64_t grb_graph_replays(const grb_context *ctx) { return ctx ? ctx->graphReplays : 0; }
+
+int32_t grb_debug_set_overflow_cap(grb_context *ctx, uint32_t entries) {
+    if (!ctx) return fail(ctx, GRB_ERR_INVALID, "null context");
+    if (int32_t r = set_device(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->overflow.p) cudaFree(ctx->overflow.p);   // re-grown at the next draw for the new stride
+    ctx->overflow.p = nullptr;
+    ctx->overflow.cap = 0;
+    ctx->overflowCap = 0;
+    ctx->overflowCapForced = entries;
     return GRB_OK;
 }
 

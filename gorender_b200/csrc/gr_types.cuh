@@ -10,8 +10,9 @@
 //   warpCount [frames][nFaceBlocks*8]     u32      slots used per warp (stage capture only)
 //   descCount [frames][nTiles]            u32      descriptors appended per tile (K2 -> K3; K3 re-zeroes)
 //   desc      [frames][nTiles][descCap]   TileDesc per-tile triangle lists, 8 B per (warp, tile) group
-//   overflow  [frames][kMaxBinsPerTri*recCap] OverflowDesc  descriptors beyond descCap (rare)
-//   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles
+//   overflow  [frames][overflowCap]       OverflowDesc  descriptors beyond descCap (rare; bounded pool)
+//   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles, and the
+//                                                  triangles of descriptors that found the pool full
 //   counters  [frames]                    FrameCounters
 //   ovl       [frames][H*W]               u64      overlay events (ShowEdges / ShowVertices only), see OverlayKey
 #pragma once
@@ -43,6 +44,8 @@ struct MeshDev {
     // fully coalesced 128-bit loads instead of gathering through the index arrays.
     const float4 *cv[3];
     const float4 *cn[3];
+    // object-space bounds of every kFaceBlock consecutive faces (mesh.cu, block_bounds_kernel)
+    const float4 *blockLo, *blockHi;
     const int32_t *vidx;     // 3 per face
     const int32_t *nidx;     // 3 per face
     const float2 *uvs;       // 3 per face
@@ -131,7 +134,8 @@ struct __align__(16) FrameCounters {
     uint32_t outOfDomain;
     uint32_t overflowCount;
     unsigned long long tpf;
-    unsigned long long pad2;
+    uint32_t listFallbacks;  // triangles sent to bigList because tile list and overflow pool were full
+    uint32_t pad2;
 };
 
 // Overlays (drawProjection's ShowEdges / ShowVertices branches, renderer.go:191-216) are written
@@ -172,6 +176,7 @@ struct DrawArgs {
     uint32_t *descCount;
     TileDesc *desc;
     OverflowDesc *overflow;
+    uint32_t overflowCap;       // entries of the overflow pool per frame
     uint32_t descCap;
     uint32_t *bigList;
     FrameCounters *counters;
@@ -180,9 +185,11 @@ struct DrawArgs {
     // target
     uchar4 *color;              // [frames][H][W]
     float *depth;               // [frames][H][W]
+    uint8_t *tileBusy;          // [frames][nTiles] 0: the tile holds the cleared background only (host mirrors skip it)
     int32_t width, height;
     int32_t ntx, nty;           // device tiles
     int32_t tileRowBegin, tileRowEnd;  // strip, in tile rows
+    int32_t rejectBlocks;       // skip face blocks whose projected bounds miss the strip / the screen (setup.cu)
     // params
     Mat4 screen;
     int32_t screenNoZ;          // screen.m[2] == 0 && screen.m[6] == 0 (NewScreenMatrix): see to_screen
@@ -193,6 +200,20 @@ struct DrawArgs {
     RefTiles ref;
     float fogStart, fogEnd;     // FrameBuffer.Fog arguments (rasterizer.go:193), GRB_OPT_FOG only
     uchar4 fogColor;
+};
+
+// One update of a host mirror pair (present.cu); every pointer is already offset to its first frame.
+struct MirrorArgs {
+    const uchar4 *color;        // device frames
+    const float *depth;
+    const uint8_t *tileBusy;    // [frames][nTiles], written by the raster kernel
+    uchar4 *hostColor;          // device-visible address of the pinned host planes (null: plane not mirrored)
+    float *hostDepth;
+    uint8_t *dirtyColor;        // [frames][nTiles] device flags: the host tile is not the cleared background
+    uint8_t *dirtyDepth;
+    unsigned long long *tilesWritten;   // statistics (may be null)
+    int32_t width, height, ntx, nty;
+    int32_t full;               // ignore tileBusy: copy every tile (framebuffers this library does not own)
 };
 
 }  // namespace gr

@@ -16,7 +16,16 @@ void launch_raster(const DrawArgs &a, int nframes, cudaStream_t s);
 // Upload time: index check + face-corner expansion (+ NewMesh's face normals), boundingBox keys.
 void launch_mesh_prepare(const MeshPrepArgs &p, cudaStream_t s);
 void launch_bbox(const float4 *verts, int nv, uint32_t *out7, cudaStream_t s);
+void launch_block_bounds(const float4 *const cv[3], int nf, float4 *blockLo, float4 *blockHi, cudaStream_t s);
 // matrixMultiplyVec4Batch over a device array.
 void launch_matvec_batch(const float m[16], float4 *vecs, long long n, cudaStream_t s);
+
+// Host mirrors: copy the tiles that are (or were) busy straight into mapped host memory.
+void launch_mirror_update(const MirrorArgs &m, int nframes, cudaStream_t s);
+
+// Hand-off flags of a framebuffer shared across processes (sort-first strips).
+void launch_signal(uint32_t *flag, uint32_t value, cudaStream_t s);
+void launch_wait_signals(uint32_t *flags, int strideWords, int n, uint32_t value, unsigned long long timeoutNs, uint32_t *timeouts,
+                         cudaStream_t s);
 
 }  // namespace gr

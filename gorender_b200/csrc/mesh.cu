@@ -89,6 +89,64 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4 *verts, int nv, 
     }
 }
 
+// Object-space bounds of every kFaceBlock consecutive faces (the unit one setup block works on): lets the
+// setup kernel skip a whole block whose projected bounds miss the rows it renders (sort-first strips) or
+// the screen.  NaN coordinates poison the block's bounds, which disables the skip for it.
+__global__ void __launch_bounds__(kFaceBlock) block_bounds_kernel(const float4 *cv0, const float4 *cv1, const float4 *cv2, int nf,
+                                                                  float4 *blockLo, float4 *blockHi) {
+    __shared__ float red[6][kFaceBlock / 32];
+    const int f = blockIdx.x * kFaceBlock + threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    bool nan = false;
+    if (f < nf) {
+        const float4 c[3] = {__ldg(&cv0[f]), __ldg(&cv1[f]), __ldg(&cv2[f])};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float v[3] = {c[k].x, c[k].y, c[k].z};
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                nan |= v[d] != v[d];
+                lo[d] = fminf(lo[d], v[d]);
+                hi[d] = fmaxf(hi[d], v[d]);
+            }
+        }
+    }
+    nan = __syncthreads_or(nan);
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[d][threadIdx.x >> 5] = lo[d];
+            red[3 + d][threadIdx.x >> 5] = hi[d];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float l[3], h[3];
+        for (int d = 0; d < 3; d++) {
+            l[d] = red[d][0];
+            h[d] = red[3 + d][0];
+            for (int w = 1; w < kFaceBlock / 32; w++) {
+                l[d] = fminf(l[d], red[d][w]);
+                h[d] = fmaxf(h[d], red[3 + d][w]);
+            }
+        }
+        const float q = __int_as_float(0x7fc00000);
+        blockLo[blockIdx.x] = nan ? make_float4(q, q, q, 1.f) : make_float4(l[0], l[1], l[2], 1.f);
+        blockHi[blockIdx.x] = nan ? make_float4(q, q, q, 1.f) : make_float4(h[0], h[1], h[2], 1.f);
+    }
+}
+
+void launch_block_bounds(const float4 *const cv[3], int nf, float4 *blockLo, float4 *blockHi, cudaStream_t s) {
+    if (nf <= 0) return;
+    block_bounds_kernel<<<(nf + kFaceBlock - 1) / kFaceBlock, kFaceBlock, 0, s>>>(cv[0], cv[1], cv[2], nf, blockLo, blockHi);
+}
+
 void launch_mesh_prepare(const MeshPrepArgs &p, cudaStream_t s) {
     if (p.nf <= 0) return;
     mesh_prepare_kernel<<<(p.nf + 255) / 256, 256, 0, s>>>(p);

@@ -1,0 +1,103 @@
+// present.cu — host mirrors of the framebuffer, kept in sync tile by tile.
+//
+// The reference's FrameBuffer lives in host memory (`Pixels`, `ZBuffer`, rasterizer.go:7-13) and every
+// Draw starts by clearing all of it (rasterizer.go:36-52).  Here the framebuffer lives in HBM, and
+// copying all of it to the caller after every frame (7.4 MB at 1280x720) makes the path PCIe-bound
+// while most of a frame is the cleared background the host already holds from the frame before.
+// A mirror is a pinned, device-mapped host plane (colour or depth) plus one byte per 32x32 tile on
+// the device: "this tile of the HOST copy is not the cleared background".  The raster kernel leaves one
+// byte per tile of every frame it renders: "this tile of the DEVICE frame is not the cleared background"
+// (DrawArgs::tileBusy).  Updating a mirror from a frame writes exactly the tiles that are busy now or
+// were busy in the host copy — straight into host memory with 128-bit stores over PCIe, no staging
+// buffer and no host-side scatter — and leaves the rest alone: background is a function of (x, y)
+// only (Clear + DotGrid), so the host plane ends up byte for byte what a full copy would have produced.
+// Measured on the box (scripts/probes/pcie_probe.cu): 46 GB/s for C3's ~130 busy tiles per frame against
+// 57 GB/s for the full-frame DMA that moves 7x the bytes; a compacted DMA plus a host scatter loop
+// stops at 5 GB/s per host core.
+
+#include "gr_types.cuh"
+#include "kernels.h"
+
+namespace gr {
+
+// One block per (tile, frame); thread t owns the 4 pixels (4 * (t & 7) .., t >> 3) of the tile, like
+// the raster kernel's write-back, so both planes move as 128-bit accesses.
+__global__ void __launch_bounds__(256) mirror_update_kernel(const MirrorArgs m) {
+    const int tile = blockIdx.x, frame = blockIdx.y;
+    const int nTiles = m.ntx * m.nty;
+    const uint8_t busy = m.full ? 1 : m.tileBusy[(size_t)frame * nTiles + tile];
+    uint8_t *dirtyC = m.dirtyColor ? m.dirtyColor + (size_t)frame * nTiles + tile : nullptr;
+    uint8_t *dirtyZ = m.dirtyDepth ? m.dirtyDepth + (size_t)frame * nTiles + tile : nullptr;
+    const bool doC = dirtyC && (busy | *dirtyC);
+    const bool doZ = dirtyZ && (busy | *dirtyZ);
+    if (!doC && !doZ) return;   // block-uniform: the host tile is background and stays background
+    const int tx = tile % m.ntx, ty = tile / m.ntx;
+    const int gx = tx * kTile + (threadIdx.x & 7) * 4, gy = ty * kTile + (threadIdx.x >> 3);
+    if (gy < m.height && gx < m.width) {
+        const size_t pix = ((size_t)frame * m.height + gy) * m.width + gx;
+        if ((m.width & 3) == 0) {
+            if (doC) *reinterpret_cast<uint4 *>(m.hostColor + pix) = *reinterpret_cast<const uint4 *>(m.color + pix);
+            if (doZ) *reinterpret_cast<float4 *>(m.hostDepth + pix) = *reinterpret_cast<const float4 *>(m.depth + pix);
+        } else {
+            for (int k = 0; k < 4 && gx + k < m.width; k++) {
+                if (doC) m.hostColor[pix + k] = m.color[pix + k];
+                if (doZ) m.hostDepth[pix + k] = m.depth[pix + k];
+            }
+        }
+    }
+    __syncthreads();   // every warp has read the flags (the early exit above is block-uniform)
+    if (threadIdx.x == 0) {
+        // nobody else touches this tile's flags in this launch
+        if (doC) *dirtyC = busy;
+        if (doZ) *dirtyZ = busy;
+        if (m.tilesWritten) atomicAdd(m.tilesWritten, (unsigned long long)((doC ? 1 : 0) + (doZ ? 1 : 0)));
+    }
+}
+
+void launch_mirror_update(const MirrorArgs &m, int nframes, cudaStream_t s) {
+    if (nframes <= 0 || m.ntx <= 0 || m.nty <= 0) return;
+    mirror_update_kernel<<<dim3(m.ntx * m.nty, nframes), 256, 0, s>>>(m);
+}
+
+// ---- cross-process hand-off flags of a shared framebuffer (sort-first strips, parallel.py) -------------
+//
+// The ranks of a strip group write their rows straight into rank 0's framebuffer over NVLink (the raster
+// kernel's 128-bit stores land in peer memory) and then raise a flag that lives next to that framebuffer;
+// rank 0's stream waits on the flags on the device, the host is not involved.  A signal is queued behind
+// the kernels whose writes it publishes; the fence orders those (complete at the kernel boundary) before
+// the flag at system scope.  The wait gives up after `timeoutNs` and counts the failure instead of
+// hanging the GPU when a peer has died.
+__global__ void signal_kernel(volatile uint32_t *flag, uint32_t value) {
+    __threadfence_system();
+    *flag = value;
+    __threadfence_system();
+}
+
+__global__ void wait_signals_kernel(volatile uint32_t *flags, int stride, int n, uint32_t value, unsigned long long timeoutNs,
+                                    uint32_t *timeouts) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    // flags only grow; signed distance so that a counter that wrapped still compares
+    while ((int32_t)(flags[(size_t)i * stride] - value) < 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeoutNs) {
+            atomicAdd(timeouts, 1u);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+void launch_signal(uint32_t *flag, uint32_t value, cudaStream_t s) { signal_kernel<<<1, 1, 0, s>>>(flag, value); }
+
+void launch_wait_signals(uint32_t *flags, int strideWords, int n, uint32_t value, unsigned long long timeoutNs, uint32_t *timeouts,
+                         cudaStream_t s) {
+    if (n <= 0) return;
+    wait_signals_kernel<<<1, 64, 0, s>>>(flags, strideWords, n, value, timeoutNs, timeouts);
+}
+
+}  // namespace gr

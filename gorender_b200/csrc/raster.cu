@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     uint32_t *descCount = a.descCount + (size_t)frame * nTiles + tile;
     const uint32_t nDescAll = *descCount;
     const uint32_t nBig = a.counters[frame].bigCount;
-    const uint32_t nOverflow = nDescAll > a.descCap ? a.counters[frame].overflowCount : 0u;
+    const uint32_t nOverflow = nDescAll > a.descCap ? min(a.counters[frame].overflowCount, a.overflowCap) : 0u;
 
     const int gx = tileX + px, gy = tileY + py;
     const bool inImage = gy < a.height && gx < a.width;
@@ -558,6 +558,9 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
         }
         empty = !__syncthreads_or(hit);
     }
+    // host mirrors (present.cu) skip tiles that hold nothing but the cleared background; with overlays or
+    // post passes any tile may differ from it
+    if (tid == 0 && a.tileBusy != nullptr) a.tileBusy[(size_t)frame * nTiles + tile] = (POST || !empty) ? 1 : 0;
     // ---- cleared background straight to HBM
     if (empty) {
         if (inImage) {
@@ -596,7 +599,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
         uint32_t *ring = fragRing[warp];
         uint32_t qHead = 0, qTail = 0;  // warp-uniform
         uint32_t win = 0;               // windows / big rounds so far (block-uniform): picks the large-triangle counter
-        const OverflowDesc *ov = a.overflow + (size_t)frame * a.recCap * kMaxBinsPerTri;
+        const OverflowDesc *ov = a.overflow + (size_t)frame * a.overflowCap;
         const uint32_t *big = a.bigList + (size_t)frame * a.recCap;
         // Rounds of up to 256 descriptors: first the tile's in-place list, then (rarely) the frame's
         // overflow list filtered by tile, finally the frame's big list as pseudo-descriptors.

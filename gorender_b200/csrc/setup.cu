@@ -255,6 +255,13 @@ __device__ __forceinline__ Emit setup_triangle(const DrawArgs &a, ScreenVert s0,
     const int nc = max(c1 - c0 + 1, 0), nr = max(r1 - r0 + 1, 0);
     e.tpf = nc * nr;
     if (e.tpf == 0) return e;
+    if (a.tileRowBegin != 0 || a.tileRowEnd != a.nty) {
+        // sort-first strips: every rank sees the triangles that touch its rows, so a triangle crossing a strip
+        // border is seen twice; its TPF is counted by the rank that owns its top row (clamped into the frame),
+        // and the ranks' TPFs add up to the frame's
+        const int oy = min(__float2int_rz(fminf(fmaxf(minY, 0.0f), 16384.0f)), a.height - 1);
+        if (oy < a.tileRowBegin * kTile || oy >= a.tileRowEnd * kTile) e.tpf = 0;
+    }
     if (!OVL && !(a.options & GRB_OPT_SHOW_FACES)) return e;
 
     bool bad = false;
@@ -316,30 +323,43 @@ __device__ __forceinline__ void store_record(const DrawArgs &a, int frame, const
     if (rec.tex >= 0) a.uv[(size_t)frame * a.recCap + slot] = uv;
 }
 
-// Appends one descriptor to a tile's list (or to the overflow list when the tile's in-place
-// segment is full).
-__device__ __forceinline__ void append_desc(const DrawArgs &a, int frame, int tile, uint32_t base, uint32_t mask) {
+// Appends one descriptor to a tile's list, or to the frame's overflow pool when the tile's in-place
+// segment is full.  The pool is bounded (DrawArgs::overflowCap): false = no room anywhere, the caller
+// sends the descriptor's triangles to the frame's big list instead, which every tile scans and which
+// has a slot for every record — correctness never depends on the pool's size.
+__device__ __forceinline__ bool append_desc(const DrawArgs &a, int frame, int tile, uint32_t base, uint32_t mask) {
     const int nTiles = a.ntx * a.nty;
     const uint32_t pos = atomicAdd(&a.descCount[(size_t)frame * nTiles + tile], 1u);
     if (pos < a.descCap) {
         a.desc[((size_t)frame * nTiles + tile) * a.descCap + pos] = {base, mask};
-    } else {
-        const uint32_t o = atomicAdd(&a.counters[frame].overflowCount, 1u);
-        a.overflow[(size_t)frame * a.recCap * kMaxBinsPerTri + o] = {(uint32_t)tile, base, mask, 0u};
+        return true;
     }
+    const uint32_t o = atomicAdd(&a.counters[frame].overflowCount, 1u);
+    if (o < a.overflowCap) {
+        a.overflow[(size_t)frame * a.overflowCap + o] = {(uint32_t)tile, base, mask, 0u};
+        return true;
+    }
+    return false;
 }
 
-// The tiles after a triangle's first one get single-triangle descriptors; triangles spanning
-// more than kMaxBinsPerTri tiles go to the frame's big list, which every tile scans.
-__device__ __forceinline__ void bin_other_tiles(const DrawArgs &a, int frame, const TileSpan &sp, uint32_t slot) {
-    if (sp.count() > kMaxBinsPerTri) {
-        const uint32_t pos = atomicAdd(&a.counters[frame].bigCount, 1u);
-        a.bigList[(size_t)frame * a.recCap + pos] = slot;
-        return;
+__device__ __forceinline__ void push_big(const DrawArgs &a, int frame, uint32_t slot) {
+    const uint32_t pos = atomicAdd(&a.counters[frame].bigCount, 1u);
+    a.bigList[(size_t)frame * a.recCap + pos] = slot;   // at most one entry per record: never full
+}
+
+// Tile lists of one emitted triangle beyond its first tile (which the caller has handled: `firstOk`
+// false = that append found no room).  Triangles spanning more than kMaxBinsPerTri tiles, and the
+// ones whose descriptors found no room, go to the frame's big list — once.
+__device__ __forceinline__ void bin_other_tiles(const DrawArgs &a, int frame, const TileSpan &sp, uint32_t slot, bool firstOk) {
+    bool ok = firstOk && sp.count() <= kMaxBinsPerTri;
+    if (ok)
+        for (int ty = sp.ty0; ty <= sp.ty1 && ok; ty++)
+            for (int tx = sp.tx0; tx <= sp.tx1 && ok; tx++)
+                if (ty != sp.ty0 || tx != sp.tx0) ok = append_desc(a, frame, ty * a.ntx + tx, slot & ~31u, 1u << (slot & 31u));
+    if (!ok) {
+        push_big(a, frame, slot);
+        if (sp.count() <= kMaxBinsPerTri) atomicAdd(&a.counters[frame].listFallbacks, 1u);
     }
-    for (int ty = sp.ty0; ty <= sp.ty1; ty++)
-        for (int tx = sp.tx0; tx <= sp.tx1; tx++)
-            if (ty != sp.ty0 || tx != sp.tx0) append_desc(a, frame, ty * a.ntx + tx, slot & ~31u, 1u << (slot & 31u));
 }
 
 // renderer.go:328-337: xyz(normalize4(world * n)) . L, with w (=1, translated)
@@ -349,6 +369,38 @@ __device__ __forceinline__ float light_intensity(const Mat4P &world, float4 n, f
     const float len = fsqrt(fadd(fadd(fadd(fmul(wn.x, wn.x), fmul(wn.y, wn.y)), fmul(wn.z, wn.z)), fmul(wn.w, wn.w)));
     const float nx = fdiv(wn.x, len), ny = fdiv(wn.y, len), nz = fdiv(wn.z, len);
     return fadd(0.5f, fmul(dot3(nx, ny, nz, lx, ly, lz), 0.5f));
+}
+
+// Sort-first strips and off-screen geometry: true when no triangle of face block `bi` can reach the rows
+// [tileRowBegin, tileRowEnd) of this draw (or the screen at all), so the whole block can retire after eight
+// vertex transforms.  The block's object-space bounds (mesh.cu) are projected corner by corner, one per
+// lane; with every corner in front of the eye (clip w < 0) the projection of the box — and of
+// everything inside it, clipped or not — lies within the corners' screen bounds.  The test is conservative
+// (2 pixels of margin against a float32 error of ~0.002 pixels; any doubt keeps the block), so results do
+// not depend on it: skipped blocks emit nothing and count no TPF on this rank.
+__device__ __forceinline__ bool block_rejected(const DrawArgs &a, const MeshDev &m, const FrameObj &fo, int bi, unsigned lane) {
+    const float4 lo = __ldg(&m.blockLo[bi]), hi = __ldg(&m.blockHi[bi]);
+    const float4 p = make_float4((lane & 1u) ? hi.x : lo.x, (lane & 2u) ? hi.y : lo.y, (lane & 4u) ? hi.z : lo.z, 1.0f);
+    const float4 c = mat_vec(fo.mvp, p);
+    float sx = fadd(fmul(a.screen.m[0], fdiv(c.x, c.w)), a.screen.m[3]);
+    float sy = fadd(fmul(a.screen.m[5], fdiv(c.y, c.w)), a.screen.m[7]);
+    const bool ok = c.w < -1e-6f && fabsf(sx) < 1e9f && fabsf(sy) < 1e9f;   // false for NaN / Inf
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    float x0 = sx, x1 = sx, y0 = sy, y1 = sy;
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    const float margin = 2.0f, W = (float)a.width, H = (float)a.height;
+    // entirely off screen: in no reference tile list (renderer.go:236-238 needs maxX >= 0, minX <= W, ...)
+    if (x1 < -margin || x0 > W + margin || y1 < -margin || y0 > H + margin) return true;
+    // rows its triangles can own (TPF) or rasterise, clamped into the frame like setup_triangle does
+    const int rlo = min(max(__float2int_rd(y0 - margin), 0), a.height - 1);
+    const int rhi = min(max(__float2int_ru(y1 + margin), 0), a.height - 1);
+    return rhi < a.tileRowBegin * kTile || rlo >= a.tileRowEnd * kTile;
 }
 
 // ---------------------------------------------------------------- K2
@@ -371,6 +423,11 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
     const MeshDev &m = a.meshes[ob.mesh];
     const unsigned lane = threadIdx.x & 31u, warpInBlock = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
+    if (!OVL && a.rejectBlocks && block_rejected(a, m, fo, fb - ob.faceBlockBase, lane)) {
+        // (the stage read-back walks every warp's slot count)
+        if (lane == 0 && a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock] = 0;
+        return;
+    }
 
     // ------------------------------------------------------------ phase 1: transform + cull
     // The MVP transform of the face's three corners (matrixMultiplyVec4Batch, renderer.go:303-304,
@@ -460,14 +517,18 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
             store_record(a, frame, e.rec, fuv, slot);
             // one descriptor (one atomic) per (first tile, 32-slot segment) group of the warp
             const unsigned binMask = __ballot_sync(validMask, !big);
+            bool firstOk = true;
             if (!big) {
                 const int t0 = sp.ty0 * a.ntx + sp.tx0;
                 const unsigned long long groupKey = ((unsigned long long)(uint32_t)t0 << 32) | (slot & ~31u);
                 const unsigned peers = __match_any_sync(binMask, groupKey);
                 const uint32_t groupMask = __reduce_or_sync(peers, 1u << (slot & 31u));
-                if ((int)lane == __ffs(peers) - 1) append_desc(a, frame, t0, slot & ~31u, groupMask);
+                const int leader = __ffs(peers) - 1;
+                int ok = 1;
+                if ((int)lane == leader) ok = append_desc(a, frame, t0, slot & ~31u, groupMask) ? 1 : 0;
+                firstOk = __shfl_sync(peers, ok, leader) != 0;
             }
-            if (big || sp.count() > 1) bin_other_tiles(a, frame, sp, slot);
+            if (big || !firstOk || sp.count() > 1) bin_other_tiles(a, frame, sp, slot, firstOk);
         } else if (alive && a.warpCount) {
             // survived the cull but draws nothing (off screen / ShowFaces off / out of domain):
             // leave an empty bbox in its slot so that the stage read-back skips it
@@ -528,8 +589,9 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
             const bool big = sp.count() > kMaxBinsPerTri;
             e.rec.order = slot;
             store_record(a, frame, e.rec, uv, slot);
-            if (!big) append_desc(a, frame, sp.ty0 * a.ntx + sp.tx0, slot & ~31u, 1u << (slot & 31u));
-            if (big || sp.count() > 1) bin_other_tiles(a, frame, sp, slot);
+            bool firstOk = true;
+            if (!big) firstOk = append_desc(a, frame, sp.ty0 * a.ntx + sp.tx0, slot & ~31u, 1u << (slot & 31u));
+            if (big || !firstOk || sp.count() > 1) bin_other_tiles(a, frame, sp, slot, firstOk);
             slot++;
         }
         if (lane == 0 && a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + warpGlobal] = slotsUsed;

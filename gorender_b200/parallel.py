@@ -6,11 +6,17 @@ Two modes, both named in BASELINE.json's north_star:
 * frame-parallel — a batch of poses is split into contiguous blocks, one per
   rank; every rank holds the whole scene and renders its frames into its own
   device framebuffers.  No data-path collective.
-* sort-first strips — rank g rasterises the tile-aligned row strip
-  `strip_rows(H, G, g)` of one large frame (geometry is replicated; K1/K2 run
-  for the whole scene on every rank, bins are clamped to the strip), then the
-  strips are gathered to rank 0: the one real exchange step of the path
-  (NCCL gather over NVLink on GPUs; gloo in the CPU tests of the host logic).
+* sort-first strips — rank g renders a tile-aligned row strip of one large
+  frame.  Geometry is replicated; the setup kernel of a rank retires every
+  256-face block whose projected bounds miss its rows after eight vertex
+  transforms (setup.cu, block_rejected), so a rank's geometry work follows its
+  share of the screen.  `StripGroup` is the B200 form of the exchange step:
+  rank 0's framebuffer is shared with the other processes (CUDA IPC), every
+  rank's raster kernel stores its rows straight into it over NVLink, and the
+  hand-off is a device-side flag per rank — no gather, no host in the loop.
+  Strips are balanced by the busy tiles of a probe frame, not by equal rows.
+  `gather_strips_to_rank0` (grouped NCCL send/recv on torch-owned framebuffers,
+  round 1's form; gloo in the CPU tests of the host logic) is kept beside it.
 """
 from __future__ import annotations
 
@@ -34,6 +40,109 @@ def strip_rows(height: int, world_size: int, rank: int, tile: int = GRB_TILE) ->
     tile_rows = (height + tile - 1) // tile
     b, e = pose_block(tile_rows, world_size, rank)
     return min(b * tile, height), min(e * tile, height)
+
+
+def balanced_strip_rows(row_weights: Sequence[float], world_size: int, height: int,
+                        tile: int = GRB_TILE) -> List[Tuple[int, int]]:
+    """Contiguous tile-aligned row ranges [y0, y1), one per rank, with about equal total weight.
+    `row_weights[r]` is the cost of tile row r (e.g. its number of busy tiles in a probe frame); rows
+    of zero weight are free and go to whichever neighbour the cut leaves them with.  Every rank gets a
+    (possibly empty) range, the ranges tile [0, height) in rank order."""
+    w = np.asarray(row_weights, dtype=np.float64)
+    n = len(w)
+    assert n == (height + tile - 1) // tile
+    total = float(w.sum())
+    if total <= 0:
+        return [strip_rows(height, world_size, r, tile) for r in range(world_size)]
+    csum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        k = int(np.searchsorted(csum, target, side="left"))      # first k with csum[k] >= target
+        if k > 0 and abs(csum[k - 1] - target) <= abs(csum[min(k, n)] - target):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), n))
+    cuts.append(n)
+    return [(min(cuts[r] * tile, height), min(cuts[r + 1] * tile, height)) for r in range(world_size)]
+
+
+class StripGroup:
+    """Sort-first strips over the ranks of a torch.distributed process group (one process per GPU of one node).
+
+    Rank 0 owns `nbuf` device framebuffers and shares them (CUDA IPC handles travel through the process
+    group as host bytes); the other ranks open them.  `draw(k, packed)` renders this rank's rows of the
+    frame into buffer k — rank 0's memory, written over NVLink by the raster kernel's own stores — and raises
+    this rank's flag; on rank 0 it also makes the render stream wait for every rank's flag, so whatever rank
+    0 queues next (a host mirror update, a read-back) sees the whole frame.  `release(k)` (rank 0) tells the
+    others that buffer k may be overwritten; `draw` on the other ranks waits for it on the device before
+    touching the buffer again.  Nothing blocks the host."""
+
+    CONSUMED_SLOT = 63
+
+    def __init__(self, device, width: int, height: int, nbuf: int = 2, group=None, rows: Optional[List[Tuple[int, int]]] = None):
+        import torch.distributed as dist
+
+        from .renderer import FrameBuffer, Renderer
+
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev, self.width, self.height = device, width, height
+        self.rows = rows if rows is not None else [strip_rows(height, self.world, r) for r in range(self.world)]
+        assert len(self.rows) == self.world
+        if self.rank == 0:
+            self.fbs = [FrameBuffer(width, height, 1, device) for _ in range(nbuf)]
+            handles = [fb.ipc_export() for fb in self.fbs] if self.world > 1 else [None] * nbuf
+        else:
+            handles = [None] * nbuf
+        if self.world > 1:
+            box = [handles]
+            dist.broadcast_object_list(box, src=0, group=group)
+            handles = box[0]
+        if self.rank != 0:
+            self.fbs = [FrameBuffer(width, height, 1, device, ipc_handle=h) for h in handles]
+        self.renderers = [Renderer(fb) for fb in self.fbs]
+        self.uses = [0] * nbuf
+        self.released = [0] * nbuf
+
+    def set_rows(self, rows: List[Tuple[int, int]]) -> None:
+        assert len(rows) == self.world
+        self.rows = rows
+
+    def draw(self, k: int, packed, timeout_ms: int = 5000):
+        """This rank's strip of the frame `packed` (grb_object[1][nobj]) into buffer k; asynchronous."""
+        fb, r = self.fbs[k], self.renderers[k]
+        n = self.uses[k] + 1
+        if self.world > 1 and self.rank != 0 and n > 1:
+            fb.wait_signals(self.CONSUMED_SLOT, 1, n - 1, timeout_ms)      # rank 0 is done with the buffer's previous frame
+        y0, y1 = self.rows[self.rank]
+        if y1 > y0:
+            r.draw_packed(packed, 0, rows=(y0, y1) if self.world > 1 else None, sync=False)
+        if self.world > 1:
+            fb.signal(self.rank, n)
+            if self.rank == 0:
+                fb.wait_signals(0, self.world, n, timeout_ms)
+        self.uses[k] = n
+        return y0, y1
+
+    def release(self, k: int) -> None:
+        """Rank 0: everything queued so far that reads buffer k comes before the other ranks' next writes into it."""
+        if self.world > 1 and self.rank == 0 and self.released[k] != self.uses[k]:
+            self.fbs[k].signal(self.CONSUMED_SLOT, self.uses[k])
+            self.released[k] = self.uses[k]
+
+    def close(self) -> None:
+        """Collective: the other ranks unmap rank 0's memory before rank 0 frees it."""
+        self.dev.synchronize()
+        if self.world > 1 and self.rank != 0:
+            for fb in self.fbs:
+                fb.close()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        if self.rank == 0:
+            for fb in self.fbs:
+                fb.close()
+        self.fbs = []
 
 
 def gather_strips_to_rank0(color, depth, height: int, group=None):

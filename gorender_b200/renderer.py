@@ -60,6 +60,9 @@ class Device:
     def synchronize(self) -> None:
         self.check(self.lib.grb_context_synchronize(self.h))
 
+    def signal_timeouts(self) -> int:
+        return int(self.lib.grb_context_signal_timeouts(self.h))
+
     def launch_count(self) -> int:
         return int(self.lib.grb_launch_count(self.h))
 
@@ -69,6 +72,16 @@ class Device:
     def set_stage_capture(self, enable: bool) -> None:
         """Also run the standalone transform kernel so `Renderer.debug_transformed` has data."""
         self.check(self.lib.grb_context_set_stage_capture(self.h, int(bool(enable))))
+
+    def set_workspace_limit(self, nbytes: int) -> None:
+        """Batches whose per-frame workspace would exceed `nbytes` are rendered in several launches."""
+        self.check(self.lib.grb_context_set_workspace_limit(self.h, int(nbytes)))
+
+    def trim(self) -> None:
+        self.check(self.lib.grb_context_trim(self.h))
+
+    def graph_replays(self) -> int:
+        return int(self.lib.grb_graph_replays(self.h))
 
     def kernel_times(self):
         ms = (C.c_double * 5)()
@@ -185,22 +198,62 @@ def default_device(device: int = 0) -> Device:
     return d
 
 
+class Mirror:
+    """A host plane (colour or depth) kept in sync with device frames tile by tile (`grb_mirror`):
+    `array` is pinned host memory of shape (frames, H, W[, 4]); `update` writes only the tiles that are
+    busy now or were busy in the host copy."""
+
+    def __init__(self, dev: Device, width: int, height: int, frames: int, plane: int):
+        self.dev = dev
+        self.plane = plane
+        shape = (frames, height, width, 4) if plane == _cabi.GRB_PLANE_COLOR else (frames, height, width)
+        self.array = dev.pinned_array(shape, np.uint8 if plane == _cabi.GRB_PLANE_COLOR else np.float32)
+        h = C.c_void_p()
+        dev.check(dev.lib.grb_mirror_create(dev.h, width, height, frames, plane, C.c_void_p(self.array.ctypes.data), C.byref(h)))
+        self.h = h
+
+    def wait(self) -> None:
+        self.dev.check(self.dev.lib.grb_mirror_wait(self.h))
+
+    def invalidate(self) -> None:
+        self.dev.check(self.dev.lib.grb_mirror_invalidate(self.h))
+
+    def stats(self) -> Tuple[int, int]:
+        """(tiles written into the host plane, tiles full copies would have moved) since creation."""
+        w, f = C.c_int64(), C.c_int64()
+        self.dev.check(self.dev.lib.grb_mirror_stats(self.h, C.byref(w), C.byref(f)))
+        return int(w.value), int(f.value)
+
+    def close(self) -> None:
+        if getattr(self, "h", None) and getattr(self.dev, "h", None):
+            self.dev.lib.grb_mirror_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FrameBuffer:
     """rasterizer.go:7-23.  `Pixels`, `Pixels2` are (H, W, 4) uint8 RGBA,
     `ZBuffer` is (H, W) float32 — host arrays, as in the reference; the device
-    copy (`frames` of them for batches) lives behind `handle`."""
+    copy (`frames` of them for batches) lives behind `handle`.  The host arrays are pinned memory
+    behind host mirrors (created on first use): `Renderer.Draw` moves only the tiles that changed."""
 
     def __init__(self, width: int, height: int, frames: int = 1, device: Optional[Device] = None,
-                 device_color: Optional[int] = None, device_depth: Optional[int] = None):
+                 device_color: Optional[int] = None, device_depth: Optional[int] = None, ipc_handle: Optional[bytes] = None):
         self.Width = int(width)
         self.Height = int(height)
         self.Frames = int(frames)
-        self.Pixels = np.zeros((height, width, 4), dtype=np.uint8)
-        self.Pixels2 = np.zeros((height, width, 4), dtype=np.uint8)
-        self.ZBuffer = np.zeros((height, width), dtype=np.float32)
         self.dev = device or default_device()
+        self._mirrors = {}   # "Pixels" / "Pixels2" / "ZBuffer" -> Mirror (one frame each)
         h = C.c_void_p()
-        if device_color is not None:
+        if ipc_handle is not None:
+            buf = (C.c_uint8 * _cabi.GRB_IPC_HANDLE_BYTES).from_buffer_copy(ipc_handle)
+            rc = self.dev.lib.grb_framebuffer_ipc_open(self.dev.h, buf, C.byref(h))
+        elif device_color is not None:
             rc = self.dev.lib.grb_framebuffer_wrap(self.dev.h, width, height, frames, C.c_void_p(device_color),
                                                    C.c_void_p(device_depth), C.byref(h))
         else:
@@ -208,9 +261,49 @@ class FrameBuffer:
         self.dev.check(rc)
         self.handle = h
 
+    def mirror(self, name: str) -> Mirror:
+        m = self._mirrors.get(name)
+        if m is None:
+            plane = _cabi.GRB_PLANE_DEPTH if name == "ZBuffer" else _cabi.GRB_PLANE_COLOR
+            m = self._mirrors[name] = Mirror(self.dev, self.Width, self.Height, 1, plane)
+            m.array[...] = 0     # the reference's NewFrameBuffer hands out zeroed slices
+        return m
+
+    @property
+    def Pixels(self) -> np.ndarray:
+        return self.mirror("Pixels").array[0]
+
+    @property
+    def Pixels2(self) -> np.ndarray:
+        return self.mirror("Pixels2").array[0]
+
+    @property
+    def ZBuffer(self) -> np.ndarray:
+        return self.mirror("ZBuffer").array[0]
+
     def SwapBuffers(self) -> None:
         """rasterizer.go:32-34."""
-        self.Pixels, self.Pixels2 = self.Pixels2, self.Pixels
+        a, b = self.mirror("Pixels"), self.mirror("Pixels2")
+        self._mirrors["Pixels"], self._mirrors["Pixels2"] = b, a
+
+    # -- a framebuffer shared by the processes of a node (sort-first strips, parallel.StripGroup)
+    def ipc_export(self) -> bytes:
+        buf = (C.c_uint8 * _cabi.GRB_IPC_HANDLE_BYTES)()
+        self.dev.check(self.dev.lib.grb_framebuffer_ipc_export(self.handle, buf))
+        return bytes(buf)
+
+    def signal(self, slot: int, value: int) -> None:
+        self.dev.check(self.dev.lib.grb_framebuffer_signal(self.dev.h, self.handle, slot, value & 0xffffffff))
+
+    def wait_signals(self, slot0: int, nslots: int, value: int, timeout_ms: int = 5000) -> None:
+        self.dev.check(self.dev.lib.grb_framebuffer_wait_signals(self.dev.h, self.handle, slot0, nslots, value & 0xffffffff, timeout_ms))
+
+    def tile_flags(self, frame: int = 0) -> np.ndarray:
+        """(tile rows, tile columns) uint8: 0 where the device tile holds only the cleared background."""
+        nty, ntx = (self.Height + _cabi.GRB_TILE - 1) // _cabi.GRB_TILE, (self.Width + _cabi.GRB_TILE - 1) // _cabi.GRB_TILE
+        out = np.zeros((nty, ntx), np.uint8)
+        self.dev.check(self.dev.lib.grb_framebuffer_read_tile_flags(self.handle, frame, C.c_void_p(out.ctypes.data)))
+        return out
 
     def device_ptrs(self) -> Tuple[int, int]:
         c, d = C.c_void_p(), C.c_void_p()
@@ -219,7 +312,7 @@ class FrameBuffer:
 
     def read(self, frame0: int = 0, nframes: int = 1, pixels: Optional[np.ndarray] = None,
              zbuffer: Optional[np.ndarray] = None, want_z: bool = True):
-        """Copy device frames to host arrays (allocated if not given)."""
+        """Copy device frames to host arrays (allocated if not given): whole frames, one DMA each."""
         if pixels is None:
             pixels = np.empty((nframes, self.Height, self.Width, 4), dtype=np.uint8)
         if zbuffer is None and want_z:
@@ -237,10 +330,21 @@ class FrameBuffer:
             C.c_void_p(pixels.ctypes.data) if pixels is not None else None,
             C.c_void_p(zbuffer.ctypes.data) if zbuffer is not None else None))
 
+    def update_mirrors_async(self, frame0: int, nframes: int, color: Optional[Mirror], depth: Optional[Mirror],
+                             color_frame0: int = 0, depth_frame0: int = 0) -> None:
+        """Bring host mirrors up to date with device frames [frame0, frame0 + nframes): only tiles that are busy
+        now or were busy in the host copy cross PCIe (grb_mirror_update_async)."""
+        self.dev.check(self.dev.lib.grb_mirror_update_async(
+            self.dev.h, self.handle, frame0, nframes, color.h if color is not None else None, color_frame0,
+            depth.h if depth is not None else None, depth_frame0))
+
     def close(self) -> None:
-        if getattr(self, "handle", None):
+        for m in getattr(self, "_mirrors", {}).values():
+            m.close()
+        self._mirrors = {}
+        if getattr(self, "handle", None) and getattr(self.dev, "h", None):
             self.dev.lib.grb_framebuffer_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -381,13 +485,18 @@ class Renderer:
         return None
 
     def Draw(self, objects: Sequence[Object], camera: Camera, read_z: bool = True) -> None:
-        """renderer.go:443-483.  Side effects: fb.Pixels, fb.ZBuffer, self.TPF."""
+        """renderer.go:443-483.  Side effects: fb.Pixels, fb.ZBuffer, self.TPF.  One C-ABI call
+        (grb_draw_present): draw, bring the host mirrors behind fb.Pixels / fb.ZBuffer up to date, stats."""
         packed = self.pack_objects(objects, [camera])
-        stats = self.draw_packed(packed, 0)
-        self.TPF = int(stats["tpf"][0])
         fb = self.fb
-        fb.read(0, 1, fb.Pixels.reshape(1, fb.Height, fb.Width, 4),
-                fb.ZBuffer.reshape(1, fb.Height, fb.Width) if read_z else None, want_z=read_z)
+        stats = np.zeros(1, dtype=_cabi.STATS_DTYPE)
+        p = self.draw_params(None)
+        color, depth = fb.mirror("Pixels"), (fb.mirror("ZBuffer") if read_z else None)
+        self.dev.check(self.dev.lib.grb_draw_present(
+            self.dev.h, fb.handle, 0, 1, C.c_void_p(packed.ctypes.data), packed.shape[1], C.byref(p),
+            color.h, 0, depth.h if depth is not None else None, 0, C.c_void_p(stats.ctypes.data)))
+        self.last_stats = stats
+        self.TPF = int(stats["tpf"][0])
 
     def DrawBatch(self, objects: Sequence[Object], cameras: Sequence[Camera],
                   rotations_y: Optional[np.ndarray] = None, read_back: bool = True, read_z: bool = True):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GRB_ABI_VERSION 2
+#define GRB_ABI_VERSION 3
 
 enum {
     GRB_OK = 0,
@@ -129,7 +129,8 @@ typedef struct grb_frame_stats {
     int32_t triangles;       /* emitted triangles that reached the rasteriser       */
     int32_t big_triangles;   /* of those, spanning more than 16 device tiles (frame-wide list) */
     int32_t out_of_domain;   /* triangles dropped: snapped |coord| > 16383 or NaN   */
-    int32_t reserved;
+    int32_t list_fallbacks;  /* triangles that went to the frame-wide list because their tile's list and the
+                                overflow pool were full (slower, never wrong)                             */
 } grb_frame_stats;
 
 /* ---- context ------------------------------------------------------------ */
@@ -157,9 +158,19 @@ int32_t grb_kernel_times(grb_context *ctx, double out_ms[5], int64_t *out_launch
 /* Total kernel launches issued by this context since creation. */
 int64_t grb_launch_count(const grb_context *ctx);
 
-/* Pinned host memory for read-back targets (cudaHostAlloc). */
+/* Per-draw workspace (records, tile lists) is sized per frame of a batch; a batch whose workspace would
+ * exceed `bytes` is rendered in several launches of fewer frames instead of failing (default: a quarter of
+ * the device's memory).  grb_context_trim frees the workspace (it is re-grown by the next draw). */
+int32_t grb_context_set_workspace_limit(grb_context *ctx, uint64_t bytes);
+int32_t grb_context_trim(grb_context *ctx);
+
+/* Pinned, device-mapped host memory for read-back targets and mirrors (cudaHostAlloc). */
 void *grb_host_alloc(uint64_t bytes);
 void grb_host_free(void *p);
+/* Pin caller-owned host memory in place (cudaHostRegister) so that it can back a mirror or an async
+ * read-back; e.g. the Go slices behind FrameBuffer.Pixels (Go's collector does not move heap objects). */
+int32_t grb_host_register(void *p, uint64_t bytes);
+int32_t grb_host_unregister(void *p);
 
 /* ---- assets (replaces nothing on the hot path: one-time upload of what
  *      LoadObjFile / NewImageTexture produced; texture.go:19-63, mesh.go:53-69) */
@@ -206,6 +217,27 @@ int32_t grb_framebuffer_wrap(grb_context *ctx, int32_t width, int32_t height, in
                              void *device_color, void *device_depth, grb_framebuffer **out);
 int32_t grb_framebuffer_destroy(grb_framebuffer *fb);
 int32_t grb_framebuffer_device_ptrs(const grb_framebuffer *fb, void **color, void **depth);
+/* One byte per GRB_TILE x GRB_TILE tile of `frame`, row-major: 0 = the tile holds only the cleared background
+ * (written by the raster kernel; 1 for tiles no draw has touched yet).  Synchronises the render stream. */
+int32_t grb_framebuffer_read_tile_flags(grb_framebuffer *fb, int32_t frame, uint8_t *out);
+
+/* ---- a framebuffer shared by the processes of one node (one per GPU): sort-first screen strips of a single
+ *      frame, every rank rasterising its rows straight into the owner's device memory over NVLink (the raster
+ *      kernel's 128-bit stores go to peer memory; no gather step).  The owner exports a handle (cudaIpc*),
+ *      the other ranks open it and draw into the result with row_begin / row_end set.  Hand-off is on the
+ *      device: 64 flag words live next to the framebuffer; grb_framebuffer_signal raises flag `slot` to `value`
+ *      behind everything queued on the caller's render stream, grb_framebuffer_wait_signals makes the
+ *      caller's render stream wait until flags [slot0, slot0 + nslots) have all reached `value` (flags only
+ *      grow).  A wait that sees no progress for `timeout_ms` gives up and is counted
+ *      (grb_context_signal_timeouts) instead of hanging the GPU. */
+#define GRB_IPC_HANDLE_BYTES 320
+#define GRB_SIGNAL_SLOTS 64
+int32_t grb_framebuffer_ipc_export(grb_framebuffer *fb, uint8_t handle[GRB_IPC_HANDLE_BYTES]);
+int32_t grb_framebuffer_ipc_open(grb_context *ctx, const uint8_t handle[GRB_IPC_HANDLE_BYTES], grb_framebuffer **out);
+int32_t grb_framebuffer_signal(grb_context *ctx, grb_framebuffer *fb, int32_t slot, uint32_t value);
+int32_t grb_framebuffer_wait_signals(grb_context *ctx, grb_framebuffer *fb, int32_t slot0, int32_t nslots, uint32_t value,
+                                     int32_t timeout_ms);
+int64_t grb_context_signal_timeouts(grb_context *ctx);
 
 /* ---- the hot path: (*Renderer).Draw (renderer.go:443-483) ----------------
  * Renders `nframes` frames into fb frames [frame0, frame0+nframes).  Every
@@ -240,6 +272,45 @@ int32_t grb_read_frames_async(grb_context *ctx, grb_framebuffer *fb, int32_t fra
  * i+1 into a second framebuffer while frame i is still crossing PCIe. */
 int32_t grb_framebuffer_wait(grb_framebuffer *fb);
 
+/* ---- host mirrors: FrameBuffer.Pixels / Pixels2 / ZBuffer (rasterizer.go:7-13) as host memory kept in
+ *      sync tile by tile.  The reference clears the whole host framebuffer at the start of every Draw
+ *      (rasterizer.go:36-52) and leaves most of it at that background; a mirror remembers, per 32x32
+ *      tile, whether the HOST plane holds anything else, the raster kernel records the same per tile of
+ *      every DEVICE frame, and an update writes only the tiles that are busy now or were busy in the
+ *      host copy — straight into the pinned plane over PCIe (no staging, no host scatter).  After the
+ *      update the plane is byte for byte what grb_read_frames would have delivered.
+ *      `host_plane`: frames * height * width * 4 bytes of memory from grb_host_alloc or pinned with
+ *      grb_host_register; its previous contents are unknown to the mirror (the first update of each frame
+ *      writes every tile).  Code that writes into the plane itself must call grb_mirror_invalidate. */
+enum { GRB_PLANE_COLOR = 0, GRB_PLANE_DEPTH = 1 };
+typedef struct grb_mirror grb_mirror;
+int32_t grb_mirror_create(grb_context *ctx, int32_t width, int32_t height, int32_t frames, int32_t plane,
+                          void *host_plane, grb_mirror **out);
+int32_t grb_mirror_destroy(grb_mirror *m);
+int32_t grb_mirror_invalidate(grb_mirror *m);
+/* Bring mirror frames [color_frame0, +nframes) / [depth_frame0, +nframes) up to date with device frames
+ * [frame0, +nframes) of `fb`.  Either mirror may be NULL.  Runs on the context's copy stream after
+ * everything queued on the render stream; a later draw into the same framebuffer waits for it. */
+int32_t grb_mirror_update_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                                grb_mirror *color, int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0);
+/* Blocks until the most recent update of `m` has landed in host memory. */
+int32_t grb_mirror_wait(grb_mirror *m);
+/* Tiles written into the host plane / tiles a full copy would have moved, since creation (synchronises). */
+int32_t grb_mirror_stats(grb_mirror *m, int64_t *tiles_written, int64_t *tiles_full);
+
+/* The literal (*Renderer).Draw (renderer.go:443-483) for a caller whose FrameBuffer is host memory:
+ * draw `nframes` frames, update the mirrors, return the stats — one call, one synchronisation.  A
+ * one-frame call replays a CUDA graph of the whole sequence (matrix upload, counters, setup, raster,
+ * mirror update, stats read-back) captured the first time this combination of scene, framebuffer,
+ * options and mirrors is seen.  Mirrors and stats may be NULL. */
+int32_t grb_draw_present(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                         const grb_object *objects, int32_t nobj, const grb_draw_params *params,
+                         grb_mirror *color, int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0,
+                         grb_frame_stats *stats);
+
+/* One-frame grb_draw_present calls served by replaying a cached CUDA graph, since context creation. */
+int64_t grb_graph_replays(const grb_context *ctx);
+
 /* ---- the build-tag seam: matrixMultiplyVec4Batch (asm_amd64.go:8-11,
  *      asm_amd64.s:7-50, asm_purego.go:9-19).  In place on n host Vec4s. */
 int32_t grb_matrix_multiply_vec4_batch(grb_context *ctx, const float m[16], float *vecs, int64_t n);
@@ -252,6 +323,9 @@ int32_t grb_debug_read_transformed(grb_context *ctx, int32_t frame, float *out, 
                                    int64_t *out_n);
 int32_t grb_debug_read_triangles(grb_context *ctx, int32_t frame, grb_triangle_rec *out, float *out_uvs /* 6 per tri, may be NULL */,
                                  int64_t capacity, int64_t *out_n);
+/* Tests of the list-fallback path: force the per-frame overflow pool to `entries` descriptors (0 = the
+ * automatic size, twice the faces of the frame).  Results never depend on it; speed does. */
+int32_t grb_debug_set_overflow_cap(grb_context *ctx, uint32_t entries);
 /* BoxVisibility (clipping.go:131-154) of each object of `frame` in the last draw. */
 int32_t grb_debug_read_visibility(grb_context *ctx, int32_t frame, int32_t *out, int32_t capacity);
 

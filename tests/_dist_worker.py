@@ -52,6 +52,12 @@ def main():
         blocks = [tuple(x.tolist()) for x in out]
         assert blocks == parallel.frame_parallel_blocks(37, world), blocks
         assert blocks[0][0] == 0 and blocks[-1][1] == 37
+        # balanced strips: computed independently on every rank from the same weights, identical everywhere
+        wts = np.array([0, 0, 3, 9, 9, 4, 0, 1, 0, 0, 0, 7], np.float64)
+        mine = parallel.balanced_strip_rows(wts, world, 12 * 32 - 5)
+        box = [None] * world
+        dist.all_gather_object(box, mine)
+        assert all(b == mine for b in box)
         dist.barrier()
         dist.destroy_process_group()
         print(f"rank {rank} ok")
@@ -75,6 +81,55 @@ def main():
             ref = orc.draw(r, sc.objects, sc.camera)
             assert np.array_equal(tfb.color[0].cpu().numpy(), ref["pixels"]), "gathered colour differs"
             assert np.array_equal(tfb.depth[0].cpu().numpy().view(np.uint32), ref["zbuffer"].view(np.uint32))
+        # ---- sort-first strips the B200 way: rank 0's framebuffers shared over CUDA IPC, every rank's raster kernel
+        #      writes its rows into them over NVLink, device-side flags hand the frame over; strips balanced by the
+        #      busy tiles of a probe frame; double-buffered; rank 0 mirrors each frame into host memory
+        probe = g.FrameBuffer(W, H, 1, dev)
+        pr = sc.renderer(probe)
+        pr.draw_packed(packed, 0)
+        weights = probe.tile_flags(0).sum(axis=1)
+        rows = parallel.balanced_strip_rows(weights, world, H)
+        assert rows[0][0] == 0 and rows[-1][1] == H and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        grp = parallel.StripGroup(dev, W, H, nbuf=2, rows=rows)
+        for rr_ in grp.renderers:
+            for k_, v_ in sc.options.items():
+                setattr(rr_, k_, v_)
+        base = [o.Translation.copy() for o in sc.objects]
+        frames = []
+        for f in range(5):
+            for o, b0 in zip(sc.objects, base):
+                o.Translation = (b0 + np.array([0.15 * f, -0.1 * f, 0], np.float32)).astype(np.float32)
+            frames.append(np.ascontiguousarray(grp.renderers[0].pack_objects(sc.objects, [sc.camera])))
+        got = []
+        for f in range(5):
+            k = f & 1
+            grp.draw(k, frames[f])
+            tpf = torch.tensor([int(0)], dtype=torch.int64, device="cuda")
+            if rank == 0:
+                fbk = grp.fbs[k]
+                fbk.update_mirrors_async(0, 1, fbk.mirror("Pixels"), fbk.mirror("ZBuffer"))   # reads the whole frame, after every rank's flag
+                grp.release(k)
+                fbk.mirror("Pixels").wait()
+                fbk.mirror("ZBuffer").wait()
+                got.append((fbk.Pixels.copy(), fbk.ZBuffer.copy()))
+            st = np.zeros(1, dtype=g._cabi.STATS_DTYPE)
+            dev.check(dev.lib.grb_frame_stats_read(dev.h, 1, st.ctypes.data))
+            y0, y1 = rows[rank]
+            tpf[0] = int(st["tpf"][0]) if y1 > y0 else 0
+            stream.synchronize()
+            dist.all_reduce(tpf)
+            if rank == 0:
+                for o, b0 in zip(sc.objects, base):
+                    o.Translation = (b0 + np.array([0.15 * f, -0.1 * f, 0], np.float32)).astype(np.float32)
+                ref = orc.draw(grp.renderers[0], sc.objects, sc.camera)
+                assert np.array_equal(got[f][0], ref["pixels"]), f"strip group frame {f}: colour differs"
+                assert np.array_equal(got[f][1].view(np.uint32), ref["zbuffer"].view(np.uint32)), f"strip group frame {f}: depth differs"
+                assert int(tpf[0]) == ref["tpf"], (int(tpf[0]), ref["tpf"])     # the ranks' TPFs add up to the frame's
+        assert dev.signal_timeouts() == 0
+        for o, b0 in zip(sc.objects, base):
+            o.Translation = b0
+        grp.close()
+        probe.close()
         # ---- frame-parallel: each rank renders its block of poses
         objs, cams = workloads.config_c5(n=16, poses=10)
         b, e = parallel.pose_block(len(cams), world, rank)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in gorender_b200.h but not exported"
     assert sorted(_cabi.SIGNATURES) == names, "ctypes signature table out of sync with the header"
-    assert lib.grb_abi_version() == _cabi.GRB_ABI_VERSION == 2
+    assert lib.grb_abi_version() == _cabi.GRB_ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():

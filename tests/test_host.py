@@ -214,3 +214,29 @@ def test_partition_arithmetic():
         assert strips[0][0] == 0 and strips[-1][1] == h
         assert all(strips[i][1] == strips[i + 1][0] for i in range(w - 1))
         assert all(b % 32 == 0 or b == h for b, _ in strips)
+
+
+def test_balanced_strip_rows_tile_the_frame():
+    """Sort-first strips balanced by per-row weights: contiguous, tile-aligned, cover the frame, and no rank gets
+    much more than its share."""
+    from gorender_b200.parallel import balanced_strip_rows, strip_rows
+
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 4, 8):
+        for h in (2160, 720, 363, 64):
+            n = (h + 31) // 32
+            for trial in range(4):
+                w = rng.integers(0, 50, n).astype(float)
+                if trial == 0:
+                    w[: n // 3] = 0
+                    w[-(n // 4):] = 0
+                rows = balanced_strip_rows(w, world, h)
+                assert len(rows) == world and rows[0][0] == 0 and rows[-1][1] == h
+                for (a0, a1), (b0, b1) in zip(rows, rows[1:]):
+                    assert a1 == b0 and a0 <= a1
+                assert all(y0 % 32 == 0 for y0, _ in rows)
+                share = [w[y0 // 32:(y1 + 31) // 32].sum() for y0, y1 in rows]
+                assert abs(sum(share) - w.sum()) < 1e-9
+                if w.sum() > 0:
+                    assert max(share) <= w.sum() / world + w.max() + 1e-9
+            assert balanced_strip_rows(np.zeros(n), world, h) == [strip_rows(h, world, r) for r in range(world)]

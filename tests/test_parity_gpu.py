@@ -177,15 +177,17 @@ def test_strips_compose_to_full_frame(strips, device, oracle):
 
     px = np.zeros((sc.height, sc.width, 4), np.uint8)
     z = np.zeros((sc.height, sc.width), np.float32)
+    tpf = 0
     for k in range(strips):
         y0, y1 = strip_rows(sc.height, strips, k)
         if y0 == y1:
             continue
         stats = r.draw_packed(packed, 0, rows=(y0, y1))
-        assert int(stats["tpf"][0]) == ref["tpf"]      # TPF does not depend on the strip
+        tpf += int(stats["tpf"][0])                    # a triangle is counted by the strip that owns its top row
         p, zz = fb.read(0, 1)
         px[y0:y1] = p[0, y0:y1]
         z[y0:y1] = zz[0, y0:y1]
+    assert tpf == ref["tpf"]                           # ... so the strips' TPFs add up to the frame's
     assert_frame_equal(px, z, ref, f"{strips} strips")
 
 
@@ -267,15 +269,66 @@ def test_full_size_c3_spin_matches_oracle(device, oracle):
         assert_frame_equal(px[f], z[f], ref, f"C3 spin frame {f}")
 
 
+def test_full_size_c4_matches_oracle(device, oracle):
+    """C4 at its BASELINE size (BASELINE.json configs[3]: 10 textured Gouraud spheres, 2.0 M faces, 3840x2160)
+    bit for bit against the oracle: the whole frame on one GPU, and the same frame composed from the 8
+    tile-aligned row strips of the sort-first mode.  The oracle renders this frame in about 0.7 s."""
+    from gorender_b200.parallel import strip_rows
+
+    objs, cam = workloads.config_c4(n=100)
+    W4, H4 = 3840, 2160
+    fb = g.FrameBuffer(W4, H4, 1, device)
+    r = g.Renderer(fb)
+    ref = oracle.draw(r, objs, cam)
+    r.Draw(objs, cam)
+    assert r.TPF == ref["tpf"]
+    assert int(r.last_stats["out_of_domain"][0]) == 0
+    assert_frame_equal(fb.Pixels, fb.ZBuffer, ref, "C4 whole frame")
+    packed = r.pack_objects(objs, [cam])
+    px = np.zeros((H4, W4, 4), np.uint8)
+    z = np.zeros((H4, W4), np.float32)
+    tpf = 0
+    for k in range(8):
+        y0, y1 = strip_rows(H4, 8, k)
+        stats = r.draw_packed(packed, 0, rows=(y0, y1))
+        tpf += int(stats["tpf"][0])
+        p, zz = fb.read(0, 1)
+        px[y0:y1] = p[0, y0:y1]
+        z[y0:y1] = zz[0, y0:y1]
+    assert tpf == ref["tpf"]
+    assert_frame_equal(px, z, ref, "C4 composed from 8 strips")
+    # ... and from 8 strips balanced by the busy tiles of the frame (what parallel.StripGroup uses)
+    from gorender_b200.parallel import balanced_strip_rows
+
+    r.draw_packed(packed, 0)
+    rows = balanced_strip_rows(fb.tile_flags(0).sum(axis=1), 8, H4)
+    px[:] = 0
+    z[:] = 0
+    tpf = 0
+    for y0, y1 in rows:
+        if y1 == y0:
+            continue
+        stats = r.draw_packed(packed, 0, rows=(y0, y1))
+        tpf += int(stats["tpf"][0])
+        p, zz = fb.read(0, 1)
+        px[y0:y1] = p[0, y0:y1]
+        z[y0:y1] = zz[0, y0:y1]
+    assert tpf == ref["tpf"]
+    assert_frame_equal(px, z, ref, "C4 composed from 8 balanced strips")
+
+
 def test_full_size_c5_pose_batch(device, oracle):
     """C5 at its BASELINE size: 4096 orbit poses of the 200k-triangle sphere at 1280x720, drawn in batches of
-    64 into alternating framebuffers.  Sampled poses are compared bit for bit with the oracle, and a
-    second pass over one batch must reproduce the first (run-to-run determinism of the atomics)."""
+    64 into alternating framebuffers.  64 poses spread over the orbit (one per batch, at a different position
+    inside each batch) are compared bit for bit with the oracle, and a second pass over one batch must
+    reproduce the first (run-to-run determinism of the atomics)."""
     objs, cams = workloads.config_c5(n=100, poses=4096)
     B = 64
     fbs = [g.FrameBuffer(1280, 720, B, device) for _ in range(2)]
     rs = [g.Renderer(fb) for fb in fbs]
-    sample = {0: None, 777: None, 2048: None, 4095: None}
+    sample = {k * B + (k * 37) % B: None for k in range(4096 // B)}
+    sample[4095] = None
+    assert len(sample) >= 64
     tpf_all = np.zeros(4096, np.int64)
     # view matrices differ per pose, the object does not move: pack once per batch
     for b0 in range(0, 4096, B):
