@@ -9,6 +9,7 @@
 // frames: setup and raster).  There is no CPU rendering path in this library.
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -130,7 +131,7 @@ struct grb_context {
     DevBuf<float4> tv;
     DevBuf<PackedRec> rec;
     DevBuf<TriUV> uv;
-    DevBuf<uint32_t> warpCount, descCount, bigList;
+    DevBuf<uint32_t> warpCount, descCount, bigList, blockList, blockCount;
     DevBuf<TileDesc> desc;
     DevBuf<OverflowDesc> overflow;
     DevBuf<FrameCounters> counters;
@@ -227,6 +228,26 @@ int box_visibility(const float4 corners[8], float zn, float zf) {
         if (outside > 0) return GRB_BOX_INTERSECT;
     }
     return GRB_BOX_INSIDE;
+}
+
+// Rows [y0, y1) of a strip draw against the projected corners of an object's bounding box: true when nothing inside
+// the box can reach them (every corner in front of the eye — clip w < 0, SURVEY H5 — and the screen-space row range,
+// two pixels of margin, clamped into the frame like the triangles' own rows, outside the strip).
+bool box_misses_rows(const float4 corners[8], const float screen[16], int height, int y0, int y1) {
+    float lo = std::numeric_limits<float>::infinity(), hi = -lo;
+    for (int c = 0; c < 8; c++) {
+        const float4 v = corners[c];
+        if (!(v.w < -1e-6f)) return false;
+        const float sy = screen[5] * (v.y / v.w) + screen[7];
+        if (!(std::fabs(sy) < 1e9f)) return false;
+        lo = std::min(lo, sy);
+        hi = std::max(hi, sy);
+    }
+    const float margin = 2.0f;
+    if (hi < -margin || lo > (float)height + margin) return false;   // off screen: BoxVisibility's business
+    const int rlo = std::min(std::max((int)std::floor(lo - margin), 0), height - 1);
+    const int rhi = std::min(std::max((int)std::ceil(hi + margin), 0), height - 1);
+    return rhi < y0 || rlo >= y1;
 }
 
 int32_t sync_tables(grb_context *ctx) {
@@ -389,6 +410,8 @@ int32_t prepare_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int3
     }
 
     const bool optClip = prm->options & GRB_OPT_FRUSTUM_CLIPPING;
+    const bool viewportShape = prm->screen[2] == 0.0f && prm->screen[6] == 0.0f && prm->screen[1] == 0.0f && prm->screen[4] == 0.0f;
+    const bool stripReject = viewportShape && !(prm->options & kOptOverlayKeys) && (rowBegin != 0 || rowEnd != nty);
     bool anyPlain = false, anyClip = false;
     uint64_t recNeed = 1, facesMax = 1;
     ctx->lastVisibility.assign((size_t)nframes * nobj, GRB_BOX_OUTSIDE);
@@ -405,7 +428,12 @@ int32_t prepare_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int3
                 const float4 p = make_float4(mh.bbox[4 * c], mh.bbox[4 * c + 1], mh.bbox[4 * c + 2], mh.bbox[4 * c + 3]);
                 corners[c] = mat_vec(src.mvp, p);  // matrixMultiplyVec4Batch(&mvpMatrix, bbox[:])
             }
-            const int vis = box_visibility(corners, prm->z_near, prm->z_far);
+            int vis = box_visibility(corners, prm->z_near, prm->z_far);
+            // sort-first strips: an object whose projected bounding box misses this draw's rows altogether is skipped
+            // like an invisible one (same conservative rule as the per-block test of the setup kernel; its triangles are
+            // drawn and counted by the ranks that own those rows)
+            if (stripReject && vis != GRB_BOX_OUTSIDE && box_misses_rows(corners, prm->screen, fb->height, rowBegin * kTile, rowEnd * kTile))
+                vis = GRB_BOX_OUTSIDE;
             dst.visibility = vis;
             dst.slotBase = (uint32_t)need;
             dst.pad[0] = dst.pad[1] = 0;
@@ -515,8 +543,14 @@ int32_t prepare_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int3
     a.screenNoZ = prm->screen[2] == 0.0f && prm->screen[6] == 0.0f;
     // block-level rejection (setup.cu) needs a NewScreenMatrix-shaped viewport (x from x/w, y from y/w only); it pays
     // when a strip is drawn or when some object reaches outside the frustum
-    a.rejectBlocks = a.screenNoZ && prm->screen[1] == 0.0f && prm->screen[4] == 0.0f && !overlayKeys &&
-                     (rowBegin != 0 || rowEnd != nty || anyClip);
+    const bool rejectBlocks = viewportShape && !overlayKeys && !ctx->stageCapture && (rowBegin != 0 || rowEnd != nty || anyClip) &&
+                              ctx->nFaceBlocks < (1 << 24);
+    if (rejectBlocks) {
+        if (int32_t r = ensure(ctx, ctx->blockList, chunk * (size_t)std::max(ctx->nFaceBlocks, 1), false)) return r;
+        if (int32_t r = ensure(ctx, ctx->blockCount, F, false)) return r;
+        a.blockList = ctx->blockList.p;
+        a.blockCount = ctx->blockCount.p;
+    }
     if (prm->ref_tiles == 1) {
         a.ref.ntx = a.ref.nty = 1;
         a.ref.tw = fb->width;
@@ -565,7 +599,7 @@ int32_t prepare_draw(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int3
 
 int launches_of(const grb_context *ctx, const DrawJob &job) {
     int per = 1;  // raster
-    if (job.anyPlain || job.anyClip) per += (ctx->stageCapture ? 1 : 0) + (job.anyPlain ? 1 : 0) + (job.anyClip ? 1 : 0);
+    if (job.anyPlain || job.anyClip) per += (ctx->stageCapture ? 1 : 0) + (job.anyPlain ? 1 : 0) + (job.anyClip ? 1 : 0) + (job.a.blockList ? 1 : 0);
     return per * ((job.nframes + job.chunk - 1) / job.chunk);
 }
 
@@ -577,6 +611,7 @@ int32_t enqueue_draw(grb_context *ctx, const DrawJob &job, bool capture) {
     CK(ctx, cudaMemcpyAsync(ctx->dFrameObjs.p, job.hfo, job.nfo * sizeof(FrameObj), cudaMemcpyHostToDevice, s));
     if (job.ring >= 0 && !capture) CK(ctx, cudaEventRecord(ctx->stagingDone[job.ring], s));
     CK(ctx, cudaMemsetAsync(ctx->counters.p, 0, F * sizeof(FrameCounters), s));
+    if (job.a.blockList) CK(ctx, cudaMemsetAsync(job.a.blockCount, 0, F * sizeof(uint32_t), s));
     const bool anyVisible = job.anyPlain || job.anyClip;
     const bool tm = ctx->timing && !capture;
     ctx->descDirty = true;
@@ -585,6 +620,7 @@ int32_t enqueue_draw(grb_context *ctx, const DrawJob &job, bool capture) {
         DrawArgs a = job.a;
         a.frameObjs += c0 * (size_t)job.nobj;
         a.counters += c0;
+        if (a.blockCount) a.blockCount += c0;
         a.color += c0 * job.npix;
         a.depth += c0 * job.npix;
         if (a.tileBusy) a.tileBusy += c0 * (size_t)job.nTiles;
@@ -593,6 +629,7 @@ int32_t enqueue_draw(grb_context *ctx, const DrawJob &job, bool capture) {
         // K1 only feeds the stage read-back (grb_debug_read_transformed); K2 transforms on its own
         if (anyVisible && ctx->stageCapture) launch_transform(a, nf, s);
         if (tm) CK(ctx, cudaEventRecord(ctx->tev[1], s));
+        if (anyVisible) launch_reject(a, nf, s);
         if (anyVisible) launch_setup(a, nf, job.anyPlain, job.anyClip, s);
         if (tm) CK(ctx, cudaEventRecord(ctx->tev[2], s));
         // (slots 2 and 3 of the timing array were the separate bin-scan / bin-fill kernels; binning
@@ -759,7 +796,7 @@ int32_t grb_context_destroy(grb_context *ctx) {
         if (t.pixels) cudaFree(t.pixels);
     void *bufs[] = {ctx->dMeshes.p, ctx->dTextures.p, ctx->dObjs.p, ctx->dVblk.p, ctx->dFblk.p, ctx->dFrameObjs.p,
                     ctx->tv.p, ctx->rec.p, ctx->uv.p, ctx->warpCount.p, ctx->descCount.p, ctx->desc.p, ctx->overflow.p,
-                    ctx->bigList.p, ctx->counters.p, ctx->seam.p, ctx->ovl.p};
+                    ctx->bigList.p, ctx->counters.p, ctx->seam.p, ctx->ovl.p, ctx->blockList.p, ctx->blockCount.p};
     for (void *p : bufs)
         if (p) cudaFree(p);
     for (int i = 0; i < kStagingRing; i++) {
@@ -835,7 +872,7 @@ int32_t grb_context_trim(grb_context *ctx) {
         b.cap = 0;
     };
     drop(ctx->tv); drop(ctx->rec); drop(ctx->uv); drop(ctx->warpCount); drop(ctx->descCount); drop(ctx->bigList);
-    drop(ctx->desc); drop(ctx->overflow); drop(ctx->ovl); drop(ctx->seam);
+    drop(ctx->desc); drop(ctx->overflow); drop(ctx->ovl); drop(ctx->seam); drop(ctx->blockList);
     ctx->recCap = 0;
     ctx->overflowCap = 0;
     ctx->lastNTiles = 0;
@@ -944,7 +981,7 @@ int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, 
     float4 *f4;
     int32_t *i32;
     float2 *f2;
-    float4 *blockLo = nullptr, *blockHi = nullptr;
+    float4 *warpLo = nullptr, *warpHi = nullptr;
     uint32_t *scratch = nullptr;   // [0..6] bbox keys + NaN bits, [7] index-check flags
     const uint32_t scratchInit[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
     uint32_t scratchHost[8];
@@ -981,13 +1018,13 @@ int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, 
         pa.cn[k] = const_cast<float4 *>(m.dev.cn[k]);
     }
     {
-        const size_t nb = ((size_t)d->nf + kFaceBlock - 1) / kFaceBlock;
-        if ((r = dev_alloc(ctx, nb, &f4, m.allocs))) goto bad;
-        m.dev.blockLo = f4;
-        blockLo = f4;
-        if ((r = dev_alloc(ctx, nb, &f4, m.allocs))) goto bad;
-        m.dev.blockHi = f4;
-        blockHi = f4;
+        const size_t nw = ((size_t)d->nf + 31) / 32;
+        if ((r = dev_alloc(ctx, nw, &f4, m.allocs))) goto bad;
+        m.dev.warpLo = f4;
+        warpLo = f4;
+        if ((r = dev_alloc(ctx, nw, &f4, m.allocs))) goto bad;
+        m.dev.warpHi = f4;
+        warpHi = f4;
     }
     if ((r = dev_alloc(ctx, (size_t)8, &scratch, m.allocs))) goto bad;
     pa.verts = m.dev.verts; pa.vnormals = m.dev.vnormals; pa.vidx = m.dev.vidx; pa.nidx = m.dev.nidx;
@@ -1000,7 +1037,7 @@ int32_t mesh_upload_impl(grb_context *ctx, const grb_mesh_desc *d, bool derive, 
         if (e == cudaSuccess) e = cudaMemcpyAsync(scratch, scratchInit, sizeof(scratchInit), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) {
             launch_mesh_prepare(pa, s);
-            launch_block_bounds(m.dev.cv, d->nf, blockLo, blockHi, s);
+            launch_warp_bounds(m.dev.cv, d->nf, warpLo, warpHi, s);
             if (derive) launch_bbox(m.dev.verts, d->nv, scratch, s);
             ctx->totalLaunches += (d->nf > 0 ? 2 : 0) + (derive ? 1 : 0);
             e = cudaGetLastError();

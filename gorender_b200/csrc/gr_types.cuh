@@ -13,6 +13,7 @@
 //   overflow  [frames][overflowCap]       OverflowDesc  descriptors beyond descCap (rare; bounded pool)
 //   bigList   [frames][recCap]            u32      triangles spanning > kMaxBinsPerTri tiles, and the
 //                                                  triangles of descriptors that found the pool full
+//   blockList [frames][nFaceBlocks]       u32      face blocks kept by reject_kernel (strip draws / partly visible objects)
 //   counters  [frames]                    FrameCounters
 //   ovl       [frames][H*W]               u64      overlay events (ShowEdges / ShowVertices only), see OverlayKey
 #pragma once
@@ -44,8 +45,8 @@ struct MeshDev {
     // fully coalesced 128-bit loads instead of gathering through the index arrays.
     const float4 *cv[3];
     const float4 *cn[3];
-    // object-space bounds of every kFaceBlock consecutive faces (mesh.cu, block_bounds_kernel)
-    const float4 *blockLo, *blockHi;
+    // object-space bounds of every 32 consecutive faces (mesh.cu, warp_bounds_kernel)
+    const float4 *warpLo, *warpHi;
     const int32_t *vidx;     // 3 per face
     const int32_t *nidx;     // 3 per face
     const float2 *uvs;       // 3 per face
@@ -189,7 +190,10 @@ struct DrawArgs {
     int32_t width, height;
     int32_t ntx, nty;           // device tiles
     int32_t tileRowBegin, tileRowEnd;  // strip, in tile rows
-    int32_t rejectBlocks;       // skip face blocks whose projected bounds miss the strip / the screen (setup.cu)
+    // face blocks (low 24 bits) and their surviving warps (high 8) kept by reject_kernel, [frames][nFaceBlocks], and
+    // their number per frame; null: every block is set up (whole-frame draws of objects inside the frustum)
+    uint32_t *blockList;
+    uint32_t *blockCount;
     // params
     Mat4 screen;
     int32_t screenNoZ;          // screen.m[2] == 0 && screen.m[6] == 0 (NewScreenMatrix): see to_screen

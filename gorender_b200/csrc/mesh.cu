@@ -89,13 +89,13 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4 *verts, int nv, 
     }
 }
 
-// Object-space bounds of every kFaceBlock consecutive faces (the unit one setup block works on): lets the
-// setup kernel skip a whole block whose projected bounds miss the rows it renders (sort-first strips) or
-// the screen.  NaN coordinates poison the block's bounds, which disables the skip for it.
-__global__ void __launch_bounds__(kFaceBlock) block_bounds_kernel(const float4 *cv0, const float4 *cv1, const float4 *cv2, int nf,
-                                                                  float4 *blockLo, float4 *blockHi) {
-    __shared__ float red[6][kFaceBlock / 32];
-    const int f = blockIdx.x * kFaceBlock + threadIdx.x;
+// Object-space bounds of every 32 consecutive faces (what one warp of a setup block works on): lets a strip draw
+// skip the warps whose faces cannot reach its rows (setup.cu, reject_kernel).  A run of 32 faces of a mesh in any
+// reasonable order is compact where 256 may straddle half the object.  NaN coordinates poison the bounds, which
+// disables the skip for that warp.
+__global__ void __launch_bounds__(256) warp_bounds_kernel(const float4 *cv0, const float4 *cv1, const float4 *cv2, int nf,
+                                                          float4 *warpLo, float4 *warpHi) {
+    const int f = blockIdx.x * 256 + threadIdx.x;
     const float inf = __int_as_float(0x7f800000);
     float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
     bool nan = false;
@@ -112,39 +112,25 @@ __global__ void __launch_bounds__(kFaceBlock) block_bounds_kernel(const float4 *
             }
         }
     }
-    nan = __syncthreads_or(nan);
+    nan = __any_sync(0xffffffffu, nan);
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
+    for (int d = 0; d < 3; d++)
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
             hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            red[d][threadIdx.x >> 5] = lo[d];
-            red[3 + d][threadIdx.x >> 5] = hi[d];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float l[3], h[3];
-        for (int d = 0; d < 3; d++) {
-            l[d] = red[d][0];
-            h[d] = red[3 + d][0];
-            for (int w = 1; w < kFaceBlock / 32; w++) {
-                l[d] = fminf(l[d], red[d][w]);
-                h[d] = fmaxf(h[d], red[3 + d][w]);
-            }
-        }
+    if ((threadIdx.x & 31) == 0 && blockIdx.x * 256 + (int)(threadIdx.x & ~31u) < nf) {
         const float q = __int_as_float(0x7fc00000);
-        blockLo[blockIdx.x] = nan ? make_float4(q, q, q, 1.f) : make_float4(l[0], l[1], l[2], 1.f);
-        blockHi[blockIdx.x] = nan ? make_float4(q, q, q, 1.f) : make_float4(h[0], h[1], h[2], 1.f);
+        const int w = f >> 5;
+        warpLo[w] = nan ? make_float4(q, q, q, 1.f) : make_float4(lo[0], lo[1], lo[2], 1.f);
+        warpHi[w] = nan ? make_float4(q, q, q, 1.f) : make_float4(hi[0], hi[1], hi[2], 1.f);
     }
 }
 
-void launch_block_bounds(const float4 *const cv[3], int nf, float4 *blockLo, float4 *blockHi, cudaStream_t s) {
+void launch_warp_bounds(const float4 *const cv[3], int nf, float4 *warpLo, float4 *warpHi, cudaStream_t s) {
     if (nf <= 0) return;
-    block_bounds_kernel<<<(nf + kFaceBlock - 1) / kFaceBlock, kFaceBlock, 0, s>>>(cv[0], cv[1], cv[2], nf, blockLo, blockHi);
+    warp_bounds_kernel<<<(nf + 255) / 256, 256, 0, s>>>(cv[0], cv[1], cv[2], nf, warpLo, warpHi);
 }
 
 void launch_mesh_prepare(const MeshPrepArgs &p, cudaStream_t s) {

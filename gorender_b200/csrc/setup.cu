@@ -371,29 +371,28 @@ __device__ __forceinline__ float light_intensity(const Mat4P &world, float4 n, f
     return fadd(0.5f, fmul(dot3(nx, ny, nz, lx, ly, lz), 0.5f));
 }
 
-// Sort-first strips and off-screen geometry: true when no triangle of face block `bi` can reach the rows
-// [tileRowBegin, tileRowEnd) of this draw (or the screen at all), so the whole block can retire after eight
-// vertex transforms.  The block's object-space bounds (mesh.cu) are projected corner by corner, one per
-// lane; with every corner in front of the eye (clip w < 0) the projection of the box — and of
-// everything inside it, clipped or not — lies within the corners' screen bounds.  The test is conservative
-// (2 pixels of margin against a float32 error of ~0.002 pixels; any doubt keeps the block), so results do
-// not depend on it: skipped blocks emit nothing and count no TPF on this rank.
-__device__ __forceinline__ bool block_rejected(const DrawArgs &a, const MeshDev &m, const FrameObj &fo, int bi, unsigned lane) {
-    const float4 lo = __ldg(&m.blockLo[bi]), hi = __ldg(&m.blockHi[bi]);
-    const float4 p = make_float4((lane & 1u) ? hi.x : lo.x, (lane & 2u) ? hi.y : lo.y, (lane & 4u) ? hi.z : lo.z, 1.0f);
-    const float4 c = mat_vec(fo.mvp, p);
-    float sx = fadd(fmul(a.screen.m[0], fdiv(c.x, c.w)), a.screen.m[3]);
-    float sy = fadd(fmul(a.screen.m[5], fdiv(c.y, c.w)), a.screen.m[7]);
-    const bool ok = c.w < -1e-6f && fabsf(sx) < 1e9f && fabsf(sy) < 1e9f;   // false for NaN / Inf
-    if (!__all_sync(0xffffffffu, ok)) return false;
-    float x0 = sx, x1 = sx, y0 = sy, y1 = sy;
+// Sort-first strips and off-screen geometry: true when nothing inside the object-space box [lo, hi] can reach the
+// rows [tileRowBegin, tileRowEnd) of this draw (or the screen at all).  The box is projected corner by corner; with
+// every corner in front of the eye (clip w < 0) the projection of the box — and of everything inside it,
+// clipped or not — lies within the corners' screen bounds.  The test is conservative (2 pixels of margin against a
+// float32 error of ~0.002 pixels, an approximate reciprocal included; any doubt keeps the box), so results do not
+// depend on it: skipped faces emit nothing and count no TPF on this rank.
+__device__ __forceinline__ bool box_rejected(const DrawArgs &a, const float *mvp, float4 lo, float4 hi) {
+    const float inf = __int_as_float(0x7f800000);
+    float x0 = inf, x1 = -inf, y0 = inf, y1 = -inf;
+    bool ok = true;
 #pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o));
-        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
-        y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    for (int k = 0; k < 8; k++) {
+        const float4 p = make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.0f);
+        const float4 c = mat_vec(mvp, p);
+        const float rw = __frcp_rn(c.w);
+        const float sx = fadd(fmul(a.screen.m[0], fmul(c.x, rw)), a.screen.m[3]);
+        const float sy = fadd(fmul(a.screen.m[5], fmul(c.y, rw)), a.screen.m[7]);
+        ok = ok && c.w < -1e-6f && fabsf(sx) < 1e9f && fabsf(sy) < 1e9f;   // false for NaN / Inf
+        x0 = fminf(x0, sx); x1 = fmaxf(x1, sx);
+        y0 = fminf(y0, sy); y1 = fmaxf(y1, sy);
     }
+    if (!ok) return false;
     const float margin = 2.0f, W = (float)a.width, H = (float)a.height;
     // entirely off screen: in no reference tile list (renderer.go:236-238 needs maxX >= 0, minX <= W, ...)
     if (x1 < -margin || x0 > W + margin || y1 < -margin || y0 > H + margin) return true;
@@ -403,14 +402,40 @@ __device__ __forceinline__ bool block_rejected(const DrawArgs &a, const MeshDev 
     return rhi < a.tileRowBegin * kTile || rlo >= a.tileRowEnd * kTile;
 }
 
+// One thread per (face block, warp of that block): tests the bounds of the warp's 32 faces (mesh.cu) and appends the
+// block with the mask of its surviving warps to the frame's block list — in any order: record slots are static, so
+// the list's order has no effect on the result.  The setup kernel then touches only what is listed.  Without this
+// pass every one of a frame's blocks pays the block prologue's chain of dependent loads before it can retire, which
+// bounds the kernel at ~25 us for the 7820 blocks of the C4 frame however little of it a strip keeps.
+__global__ void __launch_bounds__(256) reject_kernel(const __grid_constant__ DrawArgs a) {
+    const int frame = blockIdx.y;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int fb = t >> 3, w = t & 7;
+    bool keep = false;
+    if (fb < a.nFaceBlocks) {
+        const int o = a.fblkObj[fb];
+        const DrawObj ob = a.objs[o];
+        const FrameObj &fo = a.frameObjs[(size_t)frame * a.nobj + o];
+        if (fo.visibility != GRB_BOX_OUTSIDE) {
+            const MeshDev &m = a.meshes[ob.mesh];
+            const int wi = (fb - ob.faceBlockBase) * kWarpsPerFaceBlock + w;
+            if (wi * 32 < m.nf) keep = !box_rejected(a, fo.mvp, __ldg(&m.warpLo[wi]), __ldg(&m.warpHi[wi]));
+        }
+    }
+    const unsigned all = __ballot_sync(0xffffffffu, keep);
+    const unsigned mask = (all >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
+    if (w == 0 && mask != 0u && fb < a.nFaceBlocks) {
+        const uint32_t pos = atomicAdd(&a.blockCount[frame], 1u);
+        a.blockList[(size_t)frame * a.nFaceBlocks + pos] = (uint32_t)fb | (mask << 24);
+    }
+}
+
 // ---------------------------------------------------------------- K2
 
 // OVL: the instantiation that also draws the ShowEdges / ShowVertices overlays (as event keys into
 // a.ovl); the frame path proper is the OVL = false one.
 template <bool CLIP, bool OVL>
-__global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_kernel(const __grid_constant__ DrawArgs a) {
-    const int frame = blockIdx.y;
-    const int fb = blockIdx.x;
+__device__ __forceinline__ void setup_block(const DrawArgs &a, const int frame, const int fb) {
     const int o = a.fblkObj[fb];
     const DrawObj ob = a.objs[o];
     const FrameObj &fo = a.frameObjs[(size_t)frame * a.nobj + o];
@@ -423,11 +448,6 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
     const MeshDev &m = a.meshes[ob.mesh];
     const unsigned lane = threadIdx.x & 31u, warpInBlock = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
-    if (!OVL && a.rejectBlocks && block_rejected(a, m, fo, fb - ob.faceBlockBase, lane)) {
-        // (the stage read-back walks every warp's slot count)
-        if (lane == 0 && a.warpCount) a.warpCount[(size_t)frame * a.nFaceBlocks * kWarpsPerFaceBlock + (uint32_t)fb * kWarpsPerFaceBlock + warpInBlock] = 0;
-        return;
-    }
 
     // ------------------------------------------------------------ phase 1: transform + cull
     // The MVP transform of the face's three corners (matrixMultiplyVec4Batch, renderer.go:303-304,
@@ -607,11 +627,37 @@ __global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_
     }
 }
 
+// Whole-frame draws: one block per face block.
+template <bool CLIP, bool OVL>
+__global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_kernel(const __grid_constant__ DrawArgs a) {
+    setup_block<CLIP, OVL>(a, (int)blockIdx.y, (int)blockIdx.x);
+}
+
+// With a block list (strip draws, objects reaching outside the frustum: reject_kernel) a fixed grid walks the frame's
+// list — only the blocks that were kept, and of those only the warps whose 32 faces can reach this draw's rows — so
+// that a strip keeping a tenth of the frame does not launch the other nine.  (A kernel of its own: the loop costs the
+// whole-frame kernel registers it does not have.)
+template <bool CLIP>
+__global__ void __launch_bounds__(kFaceBlock, GRB_SETUP_BLOCKS) setup_list_kernel(const __grid_constant__ DrawArgs a) {
+    const int frame = blockIdx.y;
+    const uint32_t n = a.blockCount[frame];
+    const uint32_t *list = a.blockList + (size_t)frame * a.nFaceBlocks;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t entry = list[i];
+        if ((entry >> 24) >> (threadIdx.x >> 5) & 1u) setup_block<CLIP, false>(a, frame, (int)(entry & 0xffffffu));
+    }
+}
+
 // ---------------------------------------------------------------- launchers
 
 void launch_transform(const DrawArgs &a, int nframes, cudaStream_t s) {
     if (a.nVertBlocks == 0) return;
     transform_kernel<<<dim3(a.nVertBlocks, nframes), 256, 0, s>>>(a);
+}
+
+void launch_reject(const DrawArgs &a, int nframes, cudaStream_t s) {
+    if (a.nFaceBlocks == 0 || a.blockList == nullptr) return;
+    reject_kernel<<<dim3((a.nFaceBlocks * kWarpsPerFaceBlock + 255) / 256, nframes), 256, 0, s>>>(a);
 }
 
 void launch_setup(const DrawArgs &a, int nframes, bool anyPlain, bool anyClip, cudaStream_t s) {
@@ -620,6 +666,13 @@ void launch_setup(const DrawArgs &a, int nframes, bool anyPlain, bool anyClip, c
     if (a.ovl != nullptr) {
         if (anyPlain) setup_kernel<false, true><<<grid, kFaceBlock, 0, s>>>(a);
         if (anyClip) setup_kernel<true, true><<<grid, kFaceBlock, 0, s>>>(a);
+    } else if (a.blockList != nullptr) {
+        // a few blocks per SM walk the list (the setup warps are independent: no barrier to respect)
+        // two resident sets of blocks per frame walk the list (measured on the C4 strips: 13 us per frame against 16 us
+        // with one block per list entry at 8 frames per call; equal at one frame per call)
+        const dim3 lgrid(min(a.nFaceBlocks, 148 * GRB_SETUP_BLOCKS * 2), nframes);
+        if (anyPlain) setup_list_kernel<false><<<lgrid, kFaceBlock, 0, s>>>(a);
+        if (anyClip) setup_list_kernel<true><<<lgrid, kFaceBlock, 0, s>>>(a);
     } else {
         if (anyPlain) setup_kernel<false, false><<<grid, kFaceBlock, 0, s>>>(a);
         if (anyClip) setup_kernel<true, false><<<grid, kFaceBlock, 0, s>>>(a);

@@ -75,11 +75,14 @@ class StripGroup:
     this rank's flag; on rank 0 it also makes the render stream wait for every rank's flag, so whatever rank
     0 queues next (a host mirror update, a read-back) sees the whole frame.  `release(k)` (rank 0) tells the
     others that buffer k may be overwritten; `draw` on the other ranks waits for it on the device before
-    touching the buffer again.  Nothing blocks the host."""
+    touching the buffer again.  Nothing blocks the host.  A buffer may hold several consecutive frames of an
+    animation (`frames`), drawn by one call per rank: the hand-off and launch costs are then paid once per
+    call, not once per frame."""
 
     CONSUMED_SLOT = 63
 
-    def __init__(self, device, width: int, height: int, nbuf: int = 2, group=None, rows: Optional[List[Tuple[int, int]]] = None):
+    def __init__(self, device, width: int, height: int, nbuf: int = 2, group=None, rows: Optional[List[Tuple[int, int]]] = None,
+                 frames: int = 1):
         import torch.distributed as dist
 
         from .renderer import FrameBuffer, Renderer
@@ -91,7 +94,7 @@ class StripGroup:
         self.rows = rows if rows is not None else [strip_rows(height, self.world, r) for r in range(self.world)]
         assert len(self.rows) == self.world
         if self.rank == 0:
-            self.fbs = [FrameBuffer(width, height, 1, device) for _ in range(nbuf)]
+            self.fbs = [FrameBuffer(width, height, frames, device) for _ in range(nbuf)]
             handles = [fb.ipc_export() for fb in self.fbs] if self.world > 1 else [None] * nbuf
         else:
             handles = [None] * nbuf
@@ -100,7 +103,7 @@ class StripGroup:
             dist.broadcast_object_list(box, src=0, group=group)
             handles = box[0]
         if self.rank != 0:
-            self.fbs = [FrameBuffer(width, height, 1, device, ipc_handle=h) for h in handles]
+            self.fbs = [FrameBuffer(width, height, frames, device, ipc_handle=h) for h in handles]
         self.renderers = [Renderer(fb) for fb in self.fbs]
         self.uses = [0] * nbuf
         self.released = [0] * nbuf
@@ -110,7 +113,8 @@ class StripGroup:
         self.rows = rows
 
     def draw(self, k: int, packed, timeout_ms: int = 5000):
-        """This rank's strip of the frame `packed` (grb_object[1][nobj]) into buffer k; asynchronous."""
+        """This rank's strip of the frame(s) `packed` (grb_object[frames][nobj]; a buffer holds `frames` consecutive
+        frames of an animation, each split the same way) into buffer k; asynchronous."""
         fb, r = self.fbs[k], self.renderers[k]
         n = self.uses[k] + 1
         if self.world > 1 and self.rank != 0 and n > 1:
@@ -145,24 +149,27 @@ class StripGroup:
         self.fbs = []
 
 
-def gather_strips_to_rank0(color, depth, height: int, group=None):
+def gather_strips_to_rank0(color, depth, height: int, group=None, rows: Optional[List[Tuple[int, int]]] = None):
     """Gather every rank's strip of (H, W, 4) uint8 colour / (H, W) float32 depth torch tensors
     into rank 0's full-frame tensors, in place.  Strips have different heights, so this is a
-    grouped send/recv (== ncclGather with per-rank counts)."""
+    grouped send/recv (== ncclGather with per-rank counts).  `rows`: the ranks' row ranges
+    (default: equal tile rows, `strip_rows`)."""
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world == 1:
         return
+    if rows is None:
+        rows = [strip_rows(height, world, r) for r in range(world)]
     ops = []
     if rank == 0:
         for src in range(1, world):
-            y0, y1 = strip_rows(height, world, src)
+            y0, y1 = rows[src]
             if y1 > y0:
                 ops.append(dist.P2POp(dist.irecv, color[y0:y1], src, group))
                 ops.append(dist.P2POp(dist.irecv, depth[y0:y1], src, group))
     else:
-        y0, y1 = strip_rows(height, world, rank)
+        y0, y1 = rows[rank]
         if y1 > y0:
             ops.append(dist.P2POp(dist.isend, color[y0:y1], 0, group))
             ops.append(dist.P2POp(dist.isend, depth[y0:y1], 0, group))
