@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--mode", default="frames", choices=["frames", "strips"],
                     help="frames: frame-parallel C3 batches (the headline metric, with the strips leg inside for N > 1); "
                          "strips: only the sort-first strips of the 2M-triangle 3840x2160 C4 frame (strong scaling)")
-    ap.add_argument("--strips-exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--strips-exchange", default="peer", choices=["peer", "nccl", "none"],
                     help="peer: raster kernels store into rank 0's framebuffer over NVLink (StripGroup); nccl: round 1's "
                          "grouped send/recv gather")
     ap.add_argument("--strips-balance", default="busy", choices=["busy", "equal"])
@@ -496,7 +496,18 @@ def strips_leg(args, g, torch, dist, rank, world, local_rank, frames_timed=64, w
                 sfb.close()
             dist.barrier()
 
-        if exchange == "peer":
+        if exchange == "none":      # diagnostic: every rank draws its strip into its own framebuffer, nothing is exchanged
+            lfbs = [g.FrameBuffer(W4, H4, fpc, dev) for _ in range(2)]
+            lrs = [g.Renderer(fb) for fb in lfbs]
+
+            def one_frame(n):
+                y0, y1 = rows[rank]
+                if y1 > y0:
+                    lrs[n & 1].draw_packed(calls[n % FR], 0, rows=(y0, y1) if world > 1 else None, sync=False)
+
+            def finish():
+                pass
+        elif exchange == "peer":
             grp = parallel.StripGroup(dev, W4, H4, nbuf=2, rows=rows, frames=fpc)
 
             def one_frame(n):
@@ -562,11 +573,15 @@ def strips_leg(args, g, torch, dist, rank, world, local_rank, frames_timed=64, w
             ms, timeouts = float(t[0]), int(t[1])
         res = None
         if rank == 0:
-            if exchange == "peer":
+            if exchange == "none":
+                px, z = lfbs[(n - 1) & 1].read(fpc - 1, 1)
+            elif exchange == "peer":
                 px, z = grp.fbs[(n - 1) & 1].read(fpc - 1, 1)
             else:
                 px, z = tfbs[(n - 1) & 1].color[fpc - 1:].cpu().numpy(), tfbs[(n - 1) & 1].depth[fpc - 1:].cpu().numpy()
             rows_other = sum(max(0, y1 - y0) for i, (y0, y1) in enumerate(rows) if i != 0)
+            # the other ranks send rank 0 only the tiles that are busy (or were, in that buffer): background stays put
+            busy_other = int(sum(flags[y0 // 32:(y1 + 31) // 32].sum() for i, (y0, y1) in enumerate(rows) if i != 0))
             fps = frames_timed / (ms * 1e-3)
             res = {
                 "metric": "Mtriangles/s (submitted scene triangles x FPS), 2M-tri scene @3840x2160, sort-first strips",
@@ -575,7 +590,8 @@ def strips_leg(args, g, torch, dist, rank, world, local_rank, frames_timed=64, w
                 "covered_pixels": int((z[0] > -1).sum()), "checksum": int(px[0].astype(np.uint64).sum()),
                 "signal_timeouts": timeouts,
                 "rows_per_rank": [[int(a), int(b)] for a, b in rows], "busy_tiles_in_probe_frame": busy_tiles,
-                "nvlink_bytes_per_frame": int(rows_other * W4 * 8) if world > 1 else 0,
+                "nvlink_bytes_per_frame": int(busy_other * 8192) if (world > 1 and exchange == "peer") else int(rows_other * W4 * 8) if world > 1 else 0,
+                "nvlink_bytes_per_frame_if_whole_strips": int(rows_other * W4 * 8) if world > 1 else 0,
                 "workload": "C4: 10 x textured Gouraud 200k-triangle spheres, 3840x2160 (BASELINE.json configs[3])",
                 "exchange": ("every rank's raster kernel stores its rows into rank 0's framebuffer over NVLink (CUDA IPC peer memory), "
                              "device-side flags per rank, two framebuffers in flight" if exchange == "peer" else
@@ -692,19 +708,24 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     # ---- leg 2: end to end through the C ABI with host buffers: host mirrors (tile-sparse write-back into pinned
     # host memory) of every frame's pixels and z-buffer; `full` = whole-frame DMA copies instead (round 1's form)
-    mir_c = [Mirror(devs[k], WIDTH, HEIGHT, B, g._cabi.GRB_PLANE_COLOR) for k in range(2)]
-    mir_z = [Mirror(devs[k], WIDTH, HEIGHT, B, g._cabi.GRB_PLANE_DEPTH) for k in range(2)]
+    # four framebuffers (two per context) and four pairs of host planes in flight, so that a mirror update — the PCIe-bound
+    # part — always has a finished batch to move while the next ones render
+    NFB = 4
+    fbs_e = fbs + [g.FrameBuffer(WIDTH, HEIGHT, B, devs[k & 1]) for k in range(2, NFB)]
+    rends_e = rends + [g.Renderer(fb) for fb in fbs_e[2:]]
+    mir_c = [Mirror(devs[k & 1], WIDTH, HEIGHT, B, g._cabi.GRB_PLANE_COLOR) for k in range(NFB)]
+    mir_z = [Mirror(devs[k & 1], WIDTH, HEIGHT, B, g._cabi.GRB_PLANE_DEPTH) for k in range(NFB)]
     host_px = [m.array for m in mir_c]
     host_z = [m.array for m in mir_z]
 
     def step_e2e(s, with_depth=True, full=False):
         for b in range(NB):
-            k = b & 1
-            rends[k].draw_packed(packed[(s * NB + b) % nprep], 0, sync=False)   # H2D of the matrices happens inside
+            k = b % NFB
+            rends_e[k].draw_packed(packed[(s * NB + b) % nprep], 0, sync=False)   # H2D of the matrices happens inside
             if full:
-                fbs[k].read_async(0, B, host_px[k], host_z[k] if with_depth else None)  # overlaps the next draw
+                fbs_e[k].read_async(0, B, host_px[k], host_z[k] if with_depth else None)  # overlaps the next draws
             else:
-                fbs[k].update_mirrors_async(0, B, mir_c[k], mir_z[k] if with_depth else None)
+                fbs_e[k].update_mirrors_async(0, B, mir_c[k], mir_z[k] if with_depth else None)
 
     def time_e2e(steps, **kw):
         step_e2e(0, **kw)
@@ -730,7 +751,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         e2e_px_sec = time_e2e(max(1, K // 2), with_depth=False)
     tiles_w = sum(b[0] - a[0] for a, b in zip(w0, w1))
     tiles_f = sum(b[1] - a[1] for a, b in zip(w0, w1))
-    checksum = int(host_px[(NB - 1) & 1][B - 1].sum())  # the read-back is real
+    checksum = int(host_px[(NB - 1) % NFB][B - 1].sum())  # the read-back is real
 
     # ---- leg 3: per-kernel CUDA-event times (roofline of the dominant kernel)
     dev.set_kernel_timing(True)     # one context only: kernels timed back to back, no overlap
@@ -809,7 +830,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         m.close()
     host_px = host_z = None
     if not args.no_extras and world > 1:
-        for fb in fbs:
+        for fb in fbs_e:
             fb.close()
         for d in devs:
             d.trim()

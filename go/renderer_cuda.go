@@ -40,6 +40,13 @@ type cudaRenderer struct {
 	meshes   map[*Mesh]C.int32_t
 	textures map[*Texture]C.int32_t
 	objs     []C.grb_object
+	// Host mirrors of FrameBuffer.Pixels / Pixels2 / ZBuffer, keyed by the address of the slice's first
+	// element: SwapBuffers (rasterizer.go:32-34) only swaps the two slices, so the mirror of whatever
+	// fb.Pixels currently is can be looked up without touching FrameBuffer.  The slices are pinned in
+	// place once (grb_host_register; Go's collector does not move heap objects), after which a Draw moves
+	// only the 32x32 tiles that changed instead of 7.4 MB per 720p frame.
+	mirrors map[unsafe.Pointer]*C.grb_mirror
+	pending *C.grb_mirror // colour mirror of a DrawAsync still in flight
 }
 
 var (
@@ -59,7 +66,7 @@ func (r *Renderer) cuda() *cudaRenderer {
 	if s, ok := cudaStates[r]; ok {
 		return s
 	}
-	s := &cudaRenderer{meshes: map[*Mesh]C.int32_t{}, textures: map[*Texture]C.int32_t{}}
+	s := &cudaRenderer{meshes: map[*Mesh]C.int32_t{}, textures: map[*Texture]C.int32_t{}, mirrors: map[unsafe.Pointer]*C.grb_mirror{}}
 	cudaCheck(nil, C.grb_context_create(0, &s.ctx), "grb_context_create")
 	cudaCheck(s.ctx, C.grb_framebuffer_create(s.ctx, C.int32_t(r.fb.Width), C.int32_t(r.fb.Height), 1, &s.fb),
 		"grb_framebuffer_create")
@@ -176,11 +183,22 @@ func (r *Renderer) optionBits() C.uint32_t {
 	return o
 }
 
-// Draw replaces renderer.go:443-483.  Host work per object is exactly the reference's
-// renderer.go:255-265 (matrix constructors); everything else happens on the GPU.
-func (r *Renderer) Draw(objects []*Object, camera *Camera) {
-	s := r.cuda()
+// mirror returns the host mirror laid over a FrameBuffer plane (created and pinned on first use).
+func (s *cudaRenderer) mirror(r *Renderer, p unsafe.Pointer, bytes int, plane C.int32_t) *C.grb_mirror {
+	if m, ok := s.mirrors[p]; ok {
+		return m
+	}
+	if rc := C.grb_host_register(p, C.uint64_t(bytes)); rc != C.GRB_OK {
+		panic("gorender_b200: grb_host_register failed (cannot pin the framebuffer slice)")
+	}
+	var m *C.grb_mirror
+	cudaCheck(s.ctx, C.grb_mirror_create(s.ctx, C.int32_t(r.fb.Width), C.int32_t(r.fb.Height), 1, plane, p, &m), "grb_mirror_create")
+	s.mirrors[p] = m
+	return m
+}
 
+// pack fills s.objs and the draw parameters: the host work of renderer.go:255-265, unchanged.
+func (r *Renderer) pack(s *cudaRenderer, objects []*Object, camera *Camera, p *C.grb_draw_params) (*C.grb_object, C.int32_t) {
 	viewMatrix := NewViewMatrix(camera.Position, camera.Direction, camera.Up)
 	perspectiveMatrix := NewPerspectiveMatrix(r.fovY, r.aspectX, r.zNear, r.zFar)
 	if cap(s.objs) < len(objects) {
@@ -197,32 +215,63 @@ func (r *Renderer) Draw(objects []*Object, camera *Camera) {
 		matrixToC(&objs[i].world, &worldMatrix)
 		matrixToC(&objs[i].mvp, &mvpMatrix)
 	}
-
-	var p C.grb_draw_params
 	screenMatrix := NewScreenMatrix(r.fb.Width, r.fb.Height)
 	matrixToC(&p.screen, &screenMatrix)
 	light := Vec3{X: -1, Y: 1, Z: 1}.Normalize()
 	p.light[0], p.light[1], p.light[2] = C.float(light.X), C.float(light.Y), C.float(light.Z)
 	p.options = r.optionBits()
 	p.z_near, p.z_far = C.float(r.zNear), C.float(r.zFar)
-	p.ref_tiles = C.int32_t(r.numTiles) // 16 (parallel) or 1
+	// 16 (parallel) or 1.  The unmodified NewRenderer sets max(NumCPU, 16) and indexes [16]-arrays with it: on
+	// hosts with more than 16 CPUs it panics before this shim is ever reached (renderer.go:151,160; SURVEY H1) —
+	// run under `taskset -c 0-15` there.
+	p.ref_tiles = C.int32_t(min(r.numTiles, 16))
 	p.row_begin, p.row_end = 0, 0
 	// GRB_OPT_FOG is never set (the Fog call is commented out at renderer.go:479); its arguments are the ones written there
 	p.fog_start, p.fog_end = 0.100, 0.033
 	p.fog_color = [4]C.uint8_t{100, 100, 100, 255}
-
-	var stats C.grb_frame_stats
-	var objPtr *C.grb_object
-	if len(objs) > 0 {
-		objPtr = &objs[0] // grb_object holds no Go pointers: legal to pass
+	if len(objs) == 0 {
+		return nil, 0
 	}
-	cudaCheck(s.ctx, C.grb_draw(s.ctx, s.fb, 0, 1, objPtr, C.int32_t(len(objs)), &p, &stats), "grb_draw")
-	r.TPF = int(stats.tpf)
+	return &objs[0], C.int32_t(len(objs)) // grb_object holds no Go pointers: legal to pass
+}
 
-	// FrameBuffer.Pixels / ZBuffer are ordinary Go slices; C writes into them only during the call.
-	cudaCheck(s.ctx, C.grb_read_frames(s.ctx, s.fb, 0, 1,
-		(*C.uint8_t)(unsafe.Pointer(&r.fb.Pixels[0])), (*C.float)(unsafe.Pointer(&r.fb.ZBuffer[0]))),
-		"grb_read_frames")
+// Draw replaces renderer.go:443-483.  Host work per object is exactly the reference's
+// renderer.go:255-265 (matrix constructors); everything else happens on the GPU.  One C call, one
+// synchronisation: draw, bring fb.Pixels and fb.ZBuffer up to date (only the tiles that changed cross PCIe),
+// return TPF; from the second frame of a scene on it is the replay of a CUDA graph.
+func (r *Renderer) Draw(objects []*Object, camera *Camera) {
+	s := r.cuda()
+	r.WaitFrame()
+	var p C.grb_draw_params
+	objPtr, n := r.pack(s, objects, camera, &p)
+	color := s.mirror(r, unsafe.Pointer(&r.fb.Pixels[0]), 4*len(r.fb.Pixels), C.GRB_PLANE_COLOR)
+	depth := s.mirror(r, unsafe.Pointer(&r.fb.ZBuffer[0]), 4*len(r.fb.ZBuffer), C.GRB_PLANE_DEPTH)
+	var stats C.grb_frame_stats
+	cudaCheck(s.ctx, C.grb_draw_present(s.ctx, s.fb, 0, 1, objPtr, n, &p, color, 0, depth, 0, &stats), "grb_draw_present")
+	r.TPF = int(stats.tpf)
+}
+
+// DrawAsync is the streaming form for the reference's render / present loop (main.go:198-227): it queues the
+// draw and the update of fb.Pixels and returns; the frame has landed after WaitFrame (call it after
+// fb.SwapBuffers(), before reading fb.Pixels2).  fb.ZBuffer and r.TPF are not updated.
+func (r *Renderer) DrawAsync(objects []*Object, camera *Camera) {
+	s := r.cuda()
+	r.WaitFrame()
+	var p C.grb_draw_params
+	objPtr, n := r.pack(s, objects, camera, &p)
+	color := s.mirror(r, unsafe.Pointer(&r.fb.Pixels[0]), 4*len(r.fb.Pixels), C.GRB_PLANE_COLOR)
+	cudaCheck(s.ctx, C.grb_draw_async(s.ctx, s.fb, 0, 1, objPtr, n, &p), "grb_draw_async")
+	cudaCheck(s.ctx, C.grb_mirror_update_async(s.ctx, s.fb, 0, 1, color, 0, nil, 0), "grb_mirror_update_async")
+	s.pending = color
+}
+
+// WaitFrame blocks until the frame queued by the last DrawAsync is in host memory.
+func (r *Renderer) WaitFrame() {
+	s := r.cuda()
+	if s.pending != nil {
+		cudaCheck(s.ctx, C.grb_mirror_wait(s.pending), "grb_mirror_wait")
+		s.pending = nil
+	}
 }
 
 // matrixMultiplyVec4BatchCUDA is the third implementation behind the reference's build-tag seam

@@ -127,8 +127,8 @@ SIGNATURES = {
     "grb_framebuffer_destroy": (C.c_int32, [_VP]),
     "grb_framebuffer_ipc_export": (C.c_int32, [_VP, _VP]),
     "grb_framebuffer_ipc_open": (C.c_int32, [_VP, _VP, C.POINTER(_VP)]),
-    "grb_framebuffer_signal": (C.c_int32, [_VP, _VP, C.c_int32, C.c_uint32]),
-    "grb_framebuffer_wait_signals": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_uint32, C.c_int32]),
+    "grb_framebuffer_signal": (C.c_int32, [_VP, _VP, C.c_int32, C.c_uint32, C.c_int32]),
+    "grb_framebuffer_wait_signals": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_int32]),
     "grb_context_signal_timeouts": (C.c_int64, [_VP]),
     "grb_framebuffer_read_tile_flags": (C.c_int32, [_VP, C.c_int32, _VP]),
     "grb_framebuffer_device_ptrs": (C.c_int32, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
@@ -139,6 +139,8 @@ SIGNATURES = {
     "grb_read_frames_async": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     "grb_framebuffer_wait": (C.c_int32, [_VP]),
     "grb_mirror_create": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, C.POINTER(_VP)]),
+    "grb_mirror_create_on_framebuffer": (C.c_int32, [_VP, _VP, C.c_int32, C.POINTER(_VP)]),
+    "grb_mirror_update_rows_async": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32]),
     "grb_mirror_destroy": (C.c_int32, [_VP]),
     "grb_mirror_invalidate": (C.c_int32, [_VP]),
     "grb_mirror_update_async": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, C.c_int32]),

@@ -75,7 +75,8 @@ struct grb_framebuffer {
 struct grb_mirror {
     grb_context *ctx;
     int32_t width, height, frames, plane;
-    void *devPtr;                 // device-visible address of the pinned host plane
+    void *devPtr;                 // device-visible address of the plane: pinned host memory, or a framebuffer's plane
+    grb_framebuffer *target = nullptr;   // the mirror is this framebuffer's plane (a strip pushed to the frame's owner)
     uint8_t *dirty = nullptr;     // [frames][nTiles] device flags: the HOST tile is not the cleared background
     unsigned long long *tilesWritten = nullptr;   // device counter
     int64_t tilesFull = 0;        // tiles full copies would have moved
@@ -670,7 +671,7 @@ int32_t draw_impl(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t
 // ---- host mirrors (present.cu)
 
 int32_t mirror_args(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, grb_mirror *color,
-                    int32_t cf0, grb_mirror *depth, int32_t df0, MirrorArgs &m) {
+                    int32_t cf0, grb_mirror *depth, int32_t df0, int32_t rowBeginPx, int32_t rowEndPx, MirrorArgs &m) {
     std::memset(&m, 0, sizeof m);
     if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
     if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
@@ -706,6 +707,23 @@ int32_t mirror_args(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32
     m.height = fb->height;
     m.ntx = ntx;
     m.nty = nty;
+    m.tileRow0 = 0;
+    m.tileRows = nty;
+    if (!(rowBeginPx == 0 && rowEndPx == 0)) {
+        if (rowBeginPx < 0 || rowEndPx <= rowBeginPx || rowBeginPx % kTile || (rowEndPx % kTile && rowEndPx != fb->height) || rowEndPx > fb->height)
+            return fail(ctx, GRB_ERR_INVALID, "row range must be tile-aligned and inside the frame");
+        m.tileRow0 = rowBeginPx / kTile;
+        m.tileRows = (rowEndPx + kTile - 1) / kTile - m.tileRow0;
+    }
+    // a mirror that is another framebuffer's plane: keep that framebuffer's own tile flags in step
+    grb_framebuffer *target = color ? color->target : (depth ? depth->target : nullptr);
+    if (target) {
+        if ((color && color->target != target) || (depth && depth->target != target))
+            return fail(ctx, GRB_ERR_INVALID, "colour and depth mirrors belong to different framebuffers");
+        const int32_t tf0 = color ? cf0 : df0;
+        if (color && depth && cf0 != df0) return fail(ctx, GRB_ERR_INVALID, "framebuffer mirrors need the same frame offset for both planes");
+        if (target->tileBusy) m.targetBusy = target->tileBusy + (size_t)tf0 * nTiles;
+    }
     return GRB_OK;
 }
 
@@ -1266,20 +1284,20 @@ int32_t grb_framebuffer_ipc_open(grb_context *ctx, const uint8_t handle[GRB_IPC_
     return GRB_OK;
 }
 
-int32_t grb_framebuffer_signal(grb_context *ctx, grb_framebuffer *fb, int32_t slot, uint32_t value) {
+int32_t grb_framebuffer_signal(grb_context *ctx, grb_framebuffer *fb, int32_t slot, uint32_t value, int32_t on_copy_stream) {
     if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
     if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
     if (!fb->flags) return fail(ctx, GRB_ERR_STATE, "the framebuffer is not shared (grb_framebuffer_ipc_export / _open)");
     if (slot < 0 || slot >= GRB_SIGNAL_SLOTS) return fail(ctx, GRB_ERR_INVALID, "signal slot out of range");
     if (int32_t r = set_device(ctx)) return r;
-    launch_signal(fb->flags + (size_t)slot * kFlagStride, value, ctx->stream);
+    launch_signal(fb->flags + (size_t)slot * kFlagStride, value, on_copy_stream ? ctx->copyStream : ctx->stream);
     CK(ctx, cudaGetLastError());
     ctx->totalLaunches++;
     return GRB_OK;
 }
 
 int32_t grb_framebuffer_wait_signals(grb_context *ctx, grb_framebuffer *fb, int32_t slot0, int32_t nslots, uint32_t value,
-                                     int32_t timeout_ms) {
+                                     int32_t timeout_ms, int32_t on_copy_stream) {
     if (!ctx || !fb) return fail(ctx, GRB_ERR_INVALID, "null argument");
     if (fb->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
     if (!fb->flags) return fail(ctx, GRB_ERR_STATE, "the framebuffer is not shared (grb_framebuffer_ipc_export / _open)");
@@ -1291,7 +1309,8 @@ int32_t grb_framebuffer_wait_signals(grb_context *ctx, grb_framebuffer *fb, int3
         CK(ctx, cudaMemset(ctx->dTimeouts, 0, sizeof(uint32_t)));
     }
     const unsigned long long ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 5000) * 1000000ull;
-    launch_wait_signals(fb->flags + (size_t)slot0 * kFlagStride, kFlagStride, nslots, value, ns, ctx->dTimeouts, ctx->stream);
+    launch_wait_signals(fb->flags + (size_t)slot0 * kFlagStride, kFlagStride, nslots, value, ns, ctx->dTimeouts,
+                        on_copy_stream ? ctx->copyStream : ctx->stream);
     CK(ctx, cudaGetLastError());
     ctx->totalLaunches++;
     return GRB_OK;
@@ -1301,7 +1320,8 @@ int64_t grb_context_signal_timeouts(grb_context *ctx) {
     if (!ctx || !ctx->dTimeouts) return 0;
     if (set_device(ctx)) return -1;
     uint32_t n = 0;
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaMemcpy(&n, ctx->dTimeouts, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->copyStream) != cudaSuccess ||
+        cudaMemcpy(&n, ctx->dTimeouts, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
@@ -1427,6 +1447,32 @@ int32_t grb_mirror_create(grb_context *ctx, int32_t width, int32_t height, int32
     return GRB_OK;
 }
 
+int32_t grb_mirror_create_on_framebuffer(grb_context *ctx, grb_framebuffer *target, int32_t plane, grb_mirror **out) {
+    if (!ctx || !out || !target) return fail(ctx, GRB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (target->ctx != ctx) return fail(ctx, GRB_ERR_INVALID, "framebuffer belongs to another context");
+    if (plane != GRB_PLANE_COLOR && plane != GRB_PLANE_DEPTH) return fail(ctx, GRB_ERR_INVALID, "unknown plane type");
+    if (int32_t r = set_device(ctx)) return r;
+    grb_mirror *m = new grb_mirror{ctx, target->width, target->height, target->frames, plane,
+                                   plane == GRB_PLANE_COLOR ? (void *)target->color : (void *)target->depth};
+    m->target = target;
+    const size_t n = (size_t)((m->width + kTile - 1) / kTile) * ((m->height + kTile - 1) / kTile) * m->frames;
+    cudaError_t e = cudaMalloc((void **)&m->dirty, n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->tilesWritten, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->dirty, 1, n, ctx->stream);   // target contents unknown: first update writes every tile
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->tilesWritten, 0, sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (m->dirty) cudaFree(m->dirty);
+        if (m->tilesWritten) cudaFree(m->tilesWritten);
+        delete m;
+        return fail(ctx, GRB_ERR_OOM, std::string("mirror allocation: ") + cudaGetErrorString(e));
+    }
+    *out = m;
+    return GRB_OK;
+}
+
 int32_t grb_mirror_destroy(grb_mirror *m) {
     if (!m) return GRB_OK;
     grb_context *ctx = m->ctx;
@@ -1456,8 +1502,14 @@ int32_t grb_mirror_invalidate(grb_mirror *m) {
 
 int32_t grb_mirror_update_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, grb_mirror *color,
                                 int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0) {
+    return grb_mirror_update_rows_async(ctx, fb, frame0, nframes, color, color_frame0, depth, depth_frame0, 0, 0);
+}
+
+int32_t grb_mirror_update_rows_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes, grb_mirror *color,
+                                     int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0, int32_t row_begin,
+                                     int32_t row_end) {
     MirrorArgs m;
-    if (int32_t r = mirror_args(ctx, fb, frame0, nframes, color, color_frame0, depth, depth_frame0, m)) return r;
+    if (int32_t r = mirror_args(ctx, fb, frame0, nframes, color, color_frame0, depth, depth_frame0, row_begin, row_end, m)) return r;
     if (!color && !depth) return GRB_OK;
     if (int32_t r = set_device(ctx)) return r;
     cudaStream_t cs = ctx->copyStream;
@@ -1471,6 +1523,7 @@ int32_t grb_mirror_update_async(grb_context *ctx, grb_framebuffer *fb, int32_t f
         if (mm.tileBusy) mm.tileBusy += f0 * nTiles;
         if (mm.hostColor) { mm.hostColor += f0 * npix; mm.dirtyColor += f0 * nTiles; }
         if (mm.hostDepth) { mm.hostDepth += f0 * npix; mm.dirtyDepth += f0 * nTiles; }
+        if (mm.targetBusy) mm.targetBusy += f0 * nTiles;
         launch_mirror_update(mm, nf, cs);
     }
     CK(ctx, cudaGetLastError());
@@ -1480,7 +1533,7 @@ int32_t grb_mirror_update_async(grb_context *ctx, grb_framebuffer *fb, int32_t f
         if (mr) {
             CK(ctx, cudaEventRecord(mr->done, cs));
             mr->pending = true;
-            mr->tilesFull += (int64_t)m.ntx * m.nty * nframes;
+            mr->tilesFull += (int64_t)m.ntx * m.tileRows * nframes;
         }
     ctx->totalLaunches += (nframes + 32767) / 32768;
     return GRB_OK;
@@ -1518,7 +1571,7 @@ int32_t grb_draw_present(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, 
     if (int32_t r = prepare_draw(ctx, fb, frame0, nframes, objects, nobj, params, true, key.job)) return r;
     key.hasMirror = (color || depth) ? 1 : 0;
     if (key.hasMirror)
-        if (int32_t r = mirror_args(ctx, fb, frame0, nframes, color, color_frame0, depth, depth_frame0, key.m)) return r;
+        if (int32_t r = mirror_args(ctx, fb, frame0, nframes, color, color_frame0, depth, depth_frame0, 0, 0, key.m)) return r;
     if (nframes > 32768 && key.hasMirror) return fail(ctx, GRB_ERR_INVALID, "at most 32768 frames per grb_draw_present call");
     if (ctx->hCountersCap < (size_t)nframes) {
         if (ctx->hCounters) CK(ctx, cudaFreeHost(ctx->hCounters));

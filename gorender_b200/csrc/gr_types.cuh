@@ -27,7 +27,10 @@ namespace gr {
 
 constexpr int kTile = GRB_TILE;            // raster tile edge (pixels)
 constexpr int kTilePix = kTile * kTile;
-constexpr int kFaceBlock = 256;            // faces per setup block
+#ifndef GRB_FACE_BLOCK
+#define GRB_FACE_BLOCK 256
+#endif
+constexpr int kFaceBlock = GRB_FACE_BLOCK; // faces per setup block (32, 64, 128 or 256)
 constexpr int kWarpsPerFaceBlock = kFaceBlock / 32;
 constexpr int kWarpSlots = 32;             // rec slots reserved per warp, objects that do not clip
 constexpr int kWarpSlotsClip = 256;        // ... objects that clip (<= 7 triangles per face)
@@ -206,17 +209,21 @@ struct DrawArgs {
     uchar4 fogColor;
 };
 
-// One update of a host mirror pair (present.cu); every pointer is already offset to its first frame.
+// One update of a mirror pair (present.cu); every pointer is already offset to its first frame.
 struct MirrorArgs {
     const uchar4 *color;        // device frames
     const float *depth;
     const uint8_t *tileBusy;    // [frames][nTiles], written by the raster kernel
-    uchar4 *hostColor;          // device-visible address of the pinned host planes (null: plane not mirrored)
+    uchar4 *hostColor;          // device-visible address of the mirror planes: pinned host memory, or another GPU's
+                                // framebuffer (null: plane not mirrored)
     float *hostDepth;
     uint8_t *dirtyColor;        // [frames][nTiles] device flags: the host tile is not the cleared background
     uint8_t *dirtyDepth;
     unsigned long long *tilesWritten;   // statistics (may be null)
+    uint8_t *targetBusy;        // the mirror is another framebuffer (a strip pushed to its owner): that framebuffer's
+                                // own per-tile flags, kept in step so that ITS mirrors see these tiles (else null)
     int32_t width, height, ntx, nty;
+    int32_t tileRow0, tileRows; // tile rows covered by the launch (a strip), default all
     int32_t full;               // ignore tileBusy: copy every tile (framebuffers this library does not own)
 };
 

@@ -1,4 +1,4 @@
-// present.cu — host mirrors of the framebuffer, kept in sync tile by tile.
+// present.cu — mirrors of the framebuffer (host memory, or another GPU's framebuffer), kept in sync tile by tile.
 //
 // The reference's FrameBuffer lives in host memory (`Pixels`, `ZBuffer`, rasterizer.go:7-13) and every
 // Draw starts by clearing all of it (rasterizer.go:36-52).  Here the framebuffer lives in HBM, and
@@ -15,54 +15,81 @@
 // 57 GB/s for the full-frame DMA that moves 7x the bytes; a compacted DMA plus a host scatter loop
 // stops at 5 GB/s per host core.
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "gr_types.cuh"
 #include "kernels.h"
 
 namespace gr {
 
-// One block per (tile, frame); thread t owns the 4 pixels (4 * (t & 7) .., t >> 3) of the tile, like
-// the raster kernel's write-back, so both planes move as 128-bit accesses.
-__global__ void __launch_bounds__(256) mirror_update_kernel(const MirrorArgs m) {
-    const int tile = blockIdx.x, frame = blockIdx.y;
-    const int nTiles = m.ntx * m.nty;
-    const uint8_t busy = m.full ? 1 : m.tileBusy[(size_t)frame * nTiles + tile];
-    uint8_t *dirtyC = m.dirtyColor ? m.dirtyColor + (size_t)frame * nTiles + tile : nullptr;
-    uint8_t *dirtyZ = m.dirtyDepth ? m.dirtyDepth + (size_t)frame * nTiles + tile : nullptr;
-    const bool doC = dirtyC && (busy | *dirtyC);
-    const bool doZ = dirtyZ && (busy | *dirtyZ);
-    if (!doC && !doZ) return;   // block-uniform: the host tile is background and stays background
-    const int tx = tile % m.ntx, ty = tile / m.ntx;
-    const int gx = tx * kTile + (threadIdx.x & 7) * 4, gy = ty * kTile + (threadIdx.x >> 3);
-    if (gy < m.height && gx < m.width) {
-        const size_t pix = ((size_t)frame * m.height + gy) * m.width + gx;
-        if ((m.width & 3) == 0) {
-            if (doC) *reinterpret_cast<uint4 *>(m.hostColor + pix) = *reinterpret_cast<const uint4 *>(m.color + pix);
-            if (doZ) *reinterpret_cast<float4 *>(m.hostDepth + pix) = *reinterpret_cast<const float4 *>(m.depth + pix);
-        } else {
-            for (int k = 0; k < 4 && gx + k < m.width; k++) {
-                if (doC) m.hostColor[pix + k] = m.color[pix + k];
-                if (doZ) m.hostDepth[pix + k] = m.depth[pix + k];
+// A small fixed grid walks the (frame, tile) pairs; thread t owns the 4 pixels (4 * (t & 7) .., t >> 3) of the
+// tile, like the raster kernel's write-back, so both planes move as 128-bit accesses.  The grid is kept small on
+// purpose: the kernel is bound by PCIe (or NVLink), runs on the high-priority copy stream beside the render
+// kernels of the next batch, and one block per tile would fill every SM's thread slots with blocks that do
+// nothing but wait for the bus — the update would then serialise with rendering instead of hiding behind it.
+constexpr int kMirrorBlocksPerSM = 3;   // measured 1..16 on C3 beside rendering (scripts/mirror_tune.py): 3 is best by a few per cent
+
+__global__ void __launch_bounds__(256) mirror_update_kernel(const MirrorArgs m, const int nframes) {
+    const int nTiles = m.ntx * m.nty, perFrame = m.ntx * m.tileRows;
+    for (int idx = blockIdx.x; idx < nframes * perFrame; idx += gridDim.x) {
+        const int frame = idx / perFrame, tile = idx - frame * perFrame + m.tileRow0 * m.ntx;
+        const uint8_t busy = m.full ? 1 : m.tileBusy[(size_t)frame * nTiles + tile];
+        uint8_t *dirtyC = m.dirtyColor ? m.dirtyColor + (size_t)frame * nTiles + tile : nullptr;
+        uint8_t *dirtyZ = m.dirtyDepth ? m.dirtyDepth + (size_t)frame * nTiles + tile : nullptr;
+        const bool doC = dirtyC && (busy | *dirtyC);
+        const bool doZ = dirtyZ && (busy | *dirtyZ);
+        if (!doC && !doZ) continue;   // block-uniform: the mirror's tile is background and stays background
+        const int tx = tile % m.ntx, ty = tile / m.ntx;
+        const int gx = tx * kTile + (threadIdx.x & 7) * 4, gy = ty * kTile + (threadIdx.x >> 3);
+        if (gy < m.height && gx < m.width) {
+            const size_t pix = ((size_t)frame * m.height + gy) * m.width + gx;
+            if ((m.width & 3) == 0) {
+                if (doC) *reinterpret_cast<uint4 *>(m.hostColor + pix) = *reinterpret_cast<const uint4 *>(m.color + pix);
+                if (doZ) *reinterpret_cast<float4 *>(m.hostDepth + pix) = *reinterpret_cast<const float4 *>(m.depth + pix);
+            } else {
+                for (int k = 0; k < 4 && gx + k < m.width; k++) {
+                    if (doC) m.hostColor[pix + k] = m.color[pix + k];
+                    if (doZ) m.hostDepth[pix + k] = m.depth[pix + k];
+                }
             }
         }
-    }
-    __syncthreads();   // every warp has read the flags (the early exit above is block-uniform)
-    if (threadIdx.x == 0) {
-        // nobody else touches this tile's flags in this launch
-        if (doC) *dirtyC = busy;
-        if (doZ) *dirtyZ = busy;
-        if (m.tilesWritten) atomicAdd(m.tilesWritten, (unsigned long long)((doC ? 1 : 0) + (doZ ? 1 : 0)));
+        __syncthreads();   // every warp has read the flags (the skip above is block-uniform)
+        if (threadIdx.x == 0) {
+            // nobody else touches this tile's flags in this launch
+            if (doC) *dirtyC = busy;
+            if (doZ) *dirtyZ = busy;
+            if (m.targetBusy) m.targetBusy[(size_t)frame * nTiles + tile] = busy;
+            if (m.tilesWritten) atomicAdd(m.tilesWritten, (unsigned long long)((doC ? 1 : 0) + (doZ ? 1 : 0)));
+        }
     }
 }
 
 void launch_mirror_update(const MirrorArgs &m, int nframes, cudaStream_t s) {
-    if (nframes <= 0 || m.ntx <= 0 || m.nty <= 0) return;
-    mirror_update_kernel<<<dim3(m.ntx * m.nty, nframes), 256, 0, s>>>(m);
+    if (nframes <= 0 || m.ntx <= 0 || m.tileRows <= 0) return;
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    const long long total = (long long)nframes * m.ntx * m.tileRows;
+    static const int perSM = [] {   // tuning knob (scripts/mirror_tune.py)
+        const char *e = getenv("GRB_MIRROR_BLOCKS_PER_SM");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : kMirrorBlocksPerSM;
+    }();
+    const int grid = (int)std::min<long long>(total, (long long)sms * perSM);
+    mirror_update_kernel<<<grid, 256, 0, s>>>(m, nframes);
 }
 
 // ---- cross-process hand-off flags of a shared framebuffer (sort-first strips, parallel.py) -------------
 //
-// The ranks of a strip group write their rows straight into rank 0's framebuffer over NVLink (the raster
-// kernel's 128-bit stores land in peer memory) and then raise a flag that lives next to that framebuffer;
+// The same kernel is the exchange step of the sort-first strips: the mirror of a rank's local framebuffer is then
+// rank 0's framebuffer (peer memory mapped through CUDA IPC), the launch covers the rank's rows only, and the
+// tiles cross NVLink instead of PCIe — on the copy stream, while the render stream is already setting up the next
+// frames, so that rank 0's NVLink ingress (where all strips converge) is busy all the time and not only at the
+// end of every raster kernel.  Afterwards the rank raises a flag that lives next to that framebuffer;
 // rank 0's stream waits on the flags on the device, the host is not involved.  A signal is queued behind
 // the kernels whose writes it publishes; the fence orders those (complete at the kernel boundary) before
 // the flag at system scope.  The wait gives up after `timeoutNs` and counts the failure instead of

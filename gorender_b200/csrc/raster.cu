@@ -558,8 +558,8 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
         }
         empty = !__syncthreads_or(hit);
     }
-    // host mirrors (present.cu) skip tiles that hold nothing but the cleared background; with overlays or
-    // post passes any tile may differ from it
+    // host mirrors and strip pushes (present.cu) skip tiles that hold nothing but the cleared background; with
+    // overlays or post passes any tile may differ from it
     if (tid == 0 && a.tileBusy != nullptr) a.tileBusy[(size_t)frame * nTiles + tile] = (POST || !empty) ? 1 : 0;
     // ---- cleared background straight to HBM
     if (empty) {

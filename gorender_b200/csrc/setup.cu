@@ -29,7 +29,7 @@
 #include "kernels.h"
 
 #ifndef GRB_SETUP_BLOCKS
-#define GRB_SETUP_BLOCKS 5   // resident 256-thread blocks per SM the register budget is held to
+#define GRB_SETUP_BLOCKS (5 * 256 / GRB_FACE_BLOCK)   // resident blocks per SM the register budget is held to (40 warps: 48 registers)
 #endif
 
 namespace gr {
@@ -410,7 +410,7 @@ __device__ __forceinline__ bool box_rejected(const DrawArgs &a, const float *mvp
 __global__ void __launch_bounds__(256) reject_kernel(const __grid_constant__ DrawArgs a) {
     const int frame = blockIdx.y;
     const int t = blockIdx.x * 256 + threadIdx.x;
-    const int fb = t >> 3, w = t & 7;
+    const int fb = t / kWarpsPerFaceBlock, w = t % kWarpsPerFaceBlock;
     bool keep = false;
     if (fb < a.nFaceBlocks) {
         const int o = a.fblkObj[fb];
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) reject_kernel(const __grid_constant__ Dra
         }
     }
     const unsigned all = __ballot_sync(0xffffffffu, keep);
-    const unsigned mask = (all >> ((threadIdx.x & 31u) & ~7u)) & 0xffu;
+    const unsigned mask = (all >> ((threadIdx.x & 31u) & ~(unsigned)(kWarpsPerFaceBlock - 1))) & ((1u << kWarpsPerFaceBlock) - 1u);
     if (w == 0 && mask != 0u && fb < a.nFaceBlocks) {
         const uint32_t pos = atomicAdd(&a.blockCount[frame], 1u);
         a.blockList[(size_t)frame * a.nFaceBlocks + pos] = (uint32_t)fb | (mask << 24);
@@ -629,7 +629,7 @@ __device__ __forceinline__ void setup_block(const DrawArgs &a, const int frame, 
 
 // Whole-frame draws: one block per face block.
 template <bool CLIP, bool OVL>
-__global__ void __launch_bounds__(kFaceBlock, OVL ? 4 : GRB_SETUP_BLOCKS) setup_kernel(const __grid_constant__ DrawArgs a) {
+__global__ void __launch_bounds__(kFaceBlock, OVL ? 4 * 256 / GRB_FACE_BLOCK : GRB_SETUP_BLOCKS) setup_kernel(const __grid_constant__ DrawArgs a) {
     setup_block<CLIP, OVL>(a, (int)blockIdx.y, (int)blockIdx.x);
 }
 

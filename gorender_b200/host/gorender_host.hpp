@@ -671,13 +671,22 @@ struct FrameBuffer {  // rasterizer.go:7-23
     // together, so a frame still crossing PCIe into Pixels2 never blocks the draw into Pixels
     // (the reference overlaps render and present the same way, main.go:198-227).
     grb_framebuffer *handle = nullptr, *handle2 = nullptr;
+    // Host mirrors: the three host planes are kept exact tile by tile — a Draw moves only the tiles that are
+    // busy now or were busy in the plane, not 7.4 MB per 720p frame (grb_mirror_*, include/gorender_b200.h).
+    grb_mirror *mirror = nullptr, *mirror2 = nullptr, *mirrorZ = nullptr;
     FrameBuffer(Device &d, int width, int height)
         : Width(width), Height(height), ZBuffer((size_t)width * height), Pixels((size_t)width * height * 4),
           Pixels2((size_t)width * height * 4), dev(&d) {
         d.check(grb_framebuffer_create(d.ctx(), width, height, 1, &handle), "grb_framebuffer_create");
         d.check(grb_framebuffer_create(d.ctx(), width, height, 1, &handle2), "grb_framebuffer_create");
+        d.check(grb_mirror_create(d.ctx(), width, height, 1, GRB_PLANE_COLOR, Pixels.data(), &mirror), "grb_mirror_create");
+        d.check(grb_mirror_create(d.ctx(), width, height, 1, GRB_PLANE_COLOR, Pixels2.data(), &mirror2), "grb_mirror_create");
+        d.check(grb_mirror_create(d.ctx(), width, height, 1, GRB_PLANE_DEPTH, ZBuffer.data(), &mirrorZ), "grb_mirror_create");
     }
     ~FrameBuffer() {
+        grb_mirror_destroy(mirror);
+        grb_mirror_destroy(mirror2);
+        grb_mirror_destroy(mirrorZ);
         grb_framebuffer_destroy(handle);
         grb_framebuffer_destroy(handle2);
     }
@@ -687,8 +696,9 @@ struct FrameBuffer {  // rasterizer.go:7-23
     void SwapBuffers() {
         Pixels.swap(Pixels2);
         std::swap(handle, handle2);
+        std::swap(mirror, mirror2);
     }
-    void WaitFront() { dev->check(grb_framebuffer_wait(handle2), "grb_framebuffer_wait"); }
+    void WaitFront() { dev->check(grb_mirror_wait(mirror2), "grb_mirror_wait"); }
 };
 
 class Renderer {  // renderer.go:83-164
@@ -743,7 +753,7 @@ public:
         grb_draw_params p{};
         pack(objects, camera, p);
         dev.check(grb_draw_async(dev.ctx(), fb_.handle, 0, 1, objs_.empty() ? nullptr : objs_.data(), (int32_t)objs_.size(), &p), "grb_draw_async");
-        dev.check(grb_read_frames_async(dev.ctx(), fb_.handle, 0, 1, fb_.Pixels.data(), nullptr), "grb_read_frames_async");
+        dev.check(grb_mirror_update_async(dev.ctx(), fb_.handle, 0, 1, fb_.mirror, 0, nullptr, 0), "grb_mirror_update_async");
     }
 
     // renderer.go:443-483: side effects on fb.Pixels, fb.ZBuffer, TPF; throws where Go would panic
@@ -752,9 +762,11 @@ public:
         grb_draw_params p{};
         pack(objects, camera, p);
         grb_frame_stats st{};
-        dev.check(grb_draw(dev.ctx(), fb_.handle, 0, 1, objs_.empty() ? nullptr : objs_.data(), (int32_t)objs_.size(), &p, &st), "grb_draw");
+        // one call, one synchronisation: draw + host planes + stats (a CUDA graph replay after the first frame)
+        dev.check(grb_draw_present(dev.ctx(), fb_.handle, 0, 1, objs_.empty() ? nullptr : objs_.data(), (int32_t)objs_.size(), &p,
+                                   fb_.mirror, 0, fb_.mirrorZ, 0, &st),
+                  "grb_draw_present");
         TPF = (int)st.tpf;
-        dev.check(grb_read_frames(dev.ctx(), fb_.handle, 0, 1, fb_.Pixels.data(), fb_.ZBuffer.data()), "grb_read_frames");
     }
 
 private:

@@ -70,14 +70,15 @@ class StripGroup:
     """Sort-first strips over the ranks of a torch.distributed process group (one process per GPU of one node).
 
     Rank 0 owns `nbuf` device framebuffers and shares them (CUDA IPC handles travel through the process
-    group as host bytes); the other ranks open them.  `draw(k, packed)` renders this rank's rows of the
-    frame into buffer k — rank 0's memory, written over NVLink by the raster kernel's own stores — and raises
-    this rank's flag; on rank 0 it also makes the render stream wait for every rank's flag, so whatever rank
-    0 queues next (a host mirror update, a read-back) sees the whole frame.  `release(k)` (rank 0) tells the
-    others that buffer k may be overwritten; `draw` on the other ranks waits for it on the device before
-    touching the buffer again.  Nothing blocks the host.  A buffer may hold several consecutive frames of an
-    animation (`frames`), drawn by one call per rank: the hand-off and launch costs are then paid once per
-    call, not once per frame."""
+    group as host bytes); the other ranks open them.  `draw(k, packed)` renders this rank's rows of the frame(s):
+    rank 0 straight into buffer k, every other rank into a framebuffer of its own, whose rows it then pushes into
+    buffer k with a mirror laid over rank 0's memory — only the tiles that are busy (or were, in rank 0's copy)
+    cross NVLink, on the copy stream, while the render stream is already working on the next call — and raises
+    its flag.  On rank 0 `draw` also makes the render stream wait for every rank's flag, so whatever rank 0
+    queues next (a host mirror update, a read-back) sees the whole frame.  `release(k)` (rank 0) tells the others
+    that buffer k may be overwritten; their next push into it waits for that on the device.  Nothing blocks the
+    host.  A buffer may hold several consecutive frames of an animation (`frames`), drawn by one call per rank:
+    the hand-off and launch costs are then paid once per call, not once per frame."""
 
     CONSUMED_SLOT = 63
 
@@ -85,7 +86,8 @@ class StripGroup:
                  frames: int = 1):
         import torch.distributed as dist
 
-        from .renderer import FrameBuffer, Renderer
+        from ._cabi import GRB_PLANE_COLOR, GRB_PLANE_DEPTH
+        from .renderer import FrameBuffer, Mirror, Renderer
 
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -93,6 +95,7 @@ class StripGroup:
         self.dev, self.width, self.height = device, width, height
         self.rows = rows if rows is not None else [strip_rows(height, self.world, r) for r in range(self.world)]
         assert len(self.rows) == self.world
+        self.frames = frames
         if self.rank == 0:
             self.fbs = [FrameBuffer(width, height, frames, device) for _ in range(nbuf)]
             handles = [fb.ipc_export() for fb in self.fbs] if self.world > 1 else [None] * nbuf
@@ -102,30 +105,44 @@ class StripGroup:
             box = [handles]
             dist.broadcast_object_list(box, src=0, group=group)
             handles = box[0]
+        self.local, self.push = [], []
         if self.rank != 0:
-            self.fbs = [FrameBuffer(width, height, frames, device, ipc_handle=h) for h in handles]
-        self.renderers = [Renderer(fb) for fb in self.fbs]
+            self.fbs = [FrameBuffer(width, height, frames, device, ipc_handle=h) for h in handles]     # rank 0's memory
+            self.local = [FrameBuffer(width, height, frames, device) for _ in range(nbuf)]             # what this rank renders into
+            self.push = [(Mirror(device, width, height, frames, GRB_PLANE_COLOR, target=fb),
+                          Mirror(device, width, height, frames, GRB_PLANE_DEPTH, target=fb)) for fb in self.fbs]
+        self.renderers = [Renderer(fb) for fb in (self.local if self.rank != 0 else self.fbs)]
         self.uses = [0] * nbuf
         self.released = [0] * nbuf
 
     def set_rows(self, rows: List[Tuple[int, int]]) -> None:
+        """A new partition: what a rank knows about the tiles of rank 0's copy no longer covers the rows it renders."""
         assert len(rows) == self.world
         self.rows = rows
+        for mc, mz in self.push:
+            mc.invalidate()
+            mz.invalidate()
 
     def draw(self, k: int, packed, timeout_ms: int = 5000):
         """This rank's strip of the frame(s) `packed` (grb_object[frames][nobj]; a buffer holds `frames` consecutive
         frames of an animation, each split the same way) into buffer k; asynchronous."""
-        fb, r = self.fbs[k], self.renderers[k]
+        shared, r = self.fbs[k], self.renderers[k]
         n = self.uses[k] + 1
-        if self.world > 1 and self.rank != 0 and n > 1:
-            fb.wait_signals(self.CONSUMED_SLOT, 1, n - 1, timeout_ms)      # rank 0 is done with the buffer's previous frame
         y0, y1 = self.rows[self.rank]
+        nf = packed.shape[0]
         if y1 > y0:
             r.draw_packed(packed, 0, rows=(y0, y1) if self.world > 1 else None, sync=False)
         if self.world > 1:
-            fb.signal(self.rank, n)
-            if self.rank == 0:
-                fb.wait_signals(0, self.world, n, timeout_ms)
+            if self.rank != 0:
+                if n > 1:
+                    shared.wait_signals(self.CONSUMED_SLOT, 1, n - 1, timeout_ms, on_copy_stream=True)   # rank 0 is done with the buffer's previous frames
+                if y1 > y0:
+                    mc, mz = self.push[k]
+                    self.local[k].update_mirrors_async(0, nf, mc, mz, rows=(y0, y1))    # copy stream, behind the draw
+                shared.signal(self.rank, n, on_copy_stream=True)
+            else:
+                shared.signal(0, n)
+                shared.wait_signals(0, self.world, n, timeout_ms)
         self.uses[k] = n
         return y0, y1
 
@@ -139,14 +156,17 @@ class StripGroup:
         """Collective: the other ranks unmap rank 0's memory before rank 0 frees it."""
         self.dev.synchronize()
         if self.world > 1 and self.rank != 0:
-            for fb in self.fbs:
+            for mc, mz in self.push:
+                mc.close()
+                mz.close()
+            for fb in self.fbs + self.local:
                 fb.close()
         if self.world > 1:
             self.dist.barrier(group=self.group)
         if self.rank == 0:
             for fb in self.fbs:
                 fb.close()
-        self.fbs = []
+        self.fbs, self.local, self.push = [], [], []
 
 
 def gather_strips_to_rank0(color, depth, height: int, group=None, rows: Optional[List[Tuple[int, int]]] = None):

@@ -203,13 +203,20 @@ class Mirror:
     `array` is pinned host memory of shape (frames, H, W[, 4]); `update` writes only the tiles that are
     busy now or were busy in the host copy."""
 
-    def __init__(self, dev: Device, width: int, height: int, frames: int, plane: int):
+    def __init__(self, dev: Device, width: int, height: int, frames: int, plane: int, target: "Optional[FrameBuffer]" = None):
         self.dev = dev
         self.plane = plane
-        shape = (frames, height, width, 4) if plane == _cabi.GRB_PLANE_COLOR else (frames, height, width)
-        self.array = dev.pinned_array(shape, np.uint8 if plane == _cabi.GRB_PLANE_COLOR else np.float32)
         h = C.c_void_p()
-        dev.check(dev.lib.grb_mirror_create(dev.h, width, height, frames, plane, C.c_void_p(self.array.ctypes.data), C.byref(h)))
+        if target is not None:
+            # the plane is a plane of another framebuffer (normally one opened from another process: a strip pushed
+            # to the frame's owner over NVLink); there is no host array
+            self.array = None
+            self.target = target
+            dev.check(dev.lib.grb_mirror_create_on_framebuffer(dev.h, target.handle, plane, C.byref(h)))
+        else:
+            shape = (frames, height, width, 4) if plane == _cabi.GRB_PLANE_COLOR else (frames, height, width)
+            self.array = dev.pinned_array(shape, np.uint8 if plane == _cabi.GRB_PLANE_COLOR else np.float32)
+            dev.check(dev.lib.grb_mirror_create(dev.h, width, height, frames, plane, C.c_void_p(self.array.ctypes.data), C.byref(h)))
         self.h = h
 
     def wait(self) -> None:
@@ -292,11 +299,12 @@ class FrameBuffer:
         self.dev.check(self.dev.lib.grb_framebuffer_ipc_export(self.handle, buf))
         return bytes(buf)
 
-    def signal(self, slot: int, value: int) -> None:
-        self.dev.check(self.dev.lib.grb_framebuffer_signal(self.dev.h, self.handle, slot, value & 0xffffffff))
+    def signal(self, slot: int, value: int, on_copy_stream: bool = False) -> None:
+        self.dev.check(self.dev.lib.grb_framebuffer_signal(self.dev.h, self.handle, slot, value & 0xffffffff, int(on_copy_stream)))
 
-    def wait_signals(self, slot0: int, nslots: int, value: int, timeout_ms: int = 5000) -> None:
-        self.dev.check(self.dev.lib.grb_framebuffer_wait_signals(self.dev.h, self.handle, slot0, nslots, value & 0xffffffff, timeout_ms))
+    def wait_signals(self, slot0: int, nslots: int, value: int, timeout_ms: int = 5000, on_copy_stream: bool = False) -> None:
+        self.dev.check(self.dev.lib.grb_framebuffer_wait_signals(self.dev.h, self.handle, slot0, nslots, value & 0xffffffff, timeout_ms,
+                                                                 int(on_copy_stream)))
 
     def tile_flags(self, frame: int = 0) -> np.ndarray:
         """(tile rows, tile columns) uint8: 0 where the device tile holds only the cleared background."""
@@ -331,12 +339,14 @@ class FrameBuffer:
             C.c_void_p(zbuffer.ctypes.data) if zbuffer is not None else None))
 
     def update_mirrors_async(self, frame0: int, nframes: int, color: Optional[Mirror], depth: Optional[Mirror],
-                             color_frame0: int = 0, depth_frame0: int = 0) -> None:
-        """Bring host mirrors up to date with device frames [frame0, frame0 + nframes): only tiles that are busy
-        now or were busy in the host copy cross PCIe (grb_mirror_update_async)."""
-        self.dev.check(self.dev.lib.grb_mirror_update_async(
+                             color_frame0: int = 0, depth_frame0: int = 0, rows: Optional[Tuple[int, int]] = None) -> None:
+        """Bring mirrors up to date with device frames [frame0, frame0 + nframes): only tiles that are busy
+        now or were busy in the mirror's copy cross PCIe (host mirrors) or NVLink (mirrors on another GPU's
+        framebuffer); `rows` restricts the update to the tile rows a strip draw has rendered."""
+        y0, y1 = rows if rows is not None else (0, 0)
+        self.dev.check(self.dev.lib.grb_mirror_update_rows_async(
             self.dev.h, self.handle, frame0, nframes, color.h if color is not None else None, color_frame0,
-            depth.h if depth is not None else None, depth_frame0))
+            depth.h if depth is not None else None, depth_frame0, y0, y1))
 
     def close(self) -> None:
         for m in getattr(self, "_mirrors", {}).values():

@@ -221,22 +221,26 @@ int32_t grb_framebuffer_device_ptrs(const grb_framebuffer *fb, void **color, voi
  * (written by the raster kernel; 1 for tiles no draw has touched yet).  Synchronises the render stream. */
 int32_t grb_framebuffer_read_tile_flags(grb_framebuffer *fb, int32_t frame, uint8_t *out);
 
-/* ---- a framebuffer shared by the processes of one node (one per GPU): sort-first screen strips of a single
- *      frame, every rank rasterising its rows straight into the owner's device memory over NVLink (the raster
- *      kernel's 128-bit stores go to peer memory; no gather step).  The owner exports a handle (cudaIpc*),
- *      the other ranks open it and draw into the result with row_begin / row_end set.  Hand-off is on the
- *      device: 64 flag words live next to the framebuffer; grb_framebuffer_signal raises flag `slot` to `value`
- *      behind everything queued on the caller's render stream, grb_framebuffer_wait_signals makes the
- *      caller's render stream wait until flags [slot0, slot0 + nslots) have all reached `value` (flags only
- *      grow).  A wait that sees no progress for `timeout_ms` gives up and is counted
- *      (grb_context_signal_timeouts) instead of hanging the GPU. */
+/* ---- a framebuffer shared by the processes of one node (one per GPU): the exchange step of the sort-first
+ *      screen strips of a single frame.  The owner (rank 0) exports a handle (cudaIpc*), the other ranks open it.
+ *      A rank renders its rows (row_begin / row_end) into a framebuffer of its own and pushes them into the owner's
+ *      with a mirror whose plane IS the opened framebuffer (grb_mirror_create_on_framebuffer +
+ *      grb_mirror_update_rows_async): only tiles that are busy, or were busy in the owner's copy, cross NVLink, on
+ *      the copy stream, while the render stream sets up the next frames.  (Drawing straight into the opened
+ *      framebuffer also works — the raster kernel's stores then go to peer memory — but every rank's stores then
+ *      converge on the owner's NVLink ingress at the same moment, the end of its raster kernel.)  Hand-off is on
+ *      the device: 64 flag words live next to the framebuffer; grb_framebuffer_signal raises flag `slot` to `value`
+ *      behind everything queued on the caller's render stream (or copy stream), grb_framebuffer_wait_signals makes
+ *      that stream wait until flags [slot0, slot0 + nslots) have all reached `value` (flags only grow).  A wait
+ *      that sees no progress for `timeout_ms` gives up and is counted (grb_context_signal_timeouts) instead of
+ *      hanging the GPU. */
 #define GRB_IPC_HANDLE_BYTES 320
 #define GRB_SIGNAL_SLOTS 64
 int32_t grb_framebuffer_ipc_export(grb_framebuffer *fb, uint8_t handle[GRB_IPC_HANDLE_BYTES]);
 int32_t grb_framebuffer_ipc_open(grb_context *ctx, const uint8_t handle[GRB_IPC_HANDLE_BYTES], grb_framebuffer **out);
-int32_t grb_framebuffer_signal(grb_context *ctx, grb_framebuffer *fb, int32_t slot, uint32_t value);
+int32_t grb_framebuffer_signal(grb_context *ctx, grb_framebuffer *fb, int32_t slot, uint32_t value, int32_t on_copy_stream);
 int32_t grb_framebuffer_wait_signals(grb_context *ctx, grb_framebuffer *fb, int32_t slot0, int32_t nslots, uint32_t value,
-                                     int32_t timeout_ms);
+                                     int32_t timeout_ms, int32_t on_copy_stream);
 int64_t grb_context_signal_timeouts(grb_context *ctx);
 
 /* ---- the hot path: (*Renderer).Draw (renderer.go:443-483) ----------------
@@ -286,6 +290,9 @@ enum { GRB_PLANE_COLOR = 0, GRB_PLANE_DEPTH = 1 };
 typedef struct grb_mirror grb_mirror;
 int32_t grb_mirror_create(grb_context *ctx, int32_t width, int32_t height, int32_t frames, int32_t plane,
                           void *host_plane, grb_mirror **out);
+/* A mirror whose plane is a plane of `target` (normally a framebuffer opened with grb_framebuffer_ipc_open):
+ * updating it pushes tiles into that framebuffer, and keeps its per-tile background flags in step. */
+int32_t grb_mirror_create_on_framebuffer(grb_context *ctx, grb_framebuffer *target, int32_t plane, grb_mirror **out);
 int32_t grb_mirror_destroy(grb_mirror *m);
 int32_t grb_mirror_invalidate(grb_mirror *m);
 /* Bring mirror frames [color_frame0, +nframes) / [depth_frame0, +nframes) up to date with device frames
@@ -293,6 +300,11 @@ int32_t grb_mirror_invalidate(grb_mirror *m);
  * everything queued on the render stream; a later draw into the same framebuffer waits for it. */
 int32_t grb_mirror_update_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
                                 grb_mirror *color, int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0);
+/* The same for the tile rows [row_begin, row_end) only (both multiples of GRB_TILE; 0,0 = the whole frame): the
+ * rows a strip draw has rendered. */
+int32_t grb_mirror_update_rows_async(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
+                                     grb_mirror *color, int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0,
+                                     int32_t row_begin, int32_t row_end);
 /* Blocks until the most recent update of `m` has landed in host memory. */
 int32_t grb_mirror_wait(grb_mirror *m);
 /* Tiles written into the host plane / tiles a full copy would have moved, since creation (synchronises). */

@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x -k "multigpu or strips or mirror" 2>&1 | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --mode strips --steps 8 --warmup 2 > gpurun_out/strips_r02h_2gpu.json 2> gpurun_out/strips_2.err || tail -5 gpurun_out/strips_2.err
+python - <<'P'
+import json, glob
+for f in sorted(glob.glob('gpurun_out/strips_r02h_*.json')):
+    d = json.load(open(f))
+    print(f, round(d['value']), 'Mtri/s', round(d['ms_per_frame']*1e3,1), 'us/frame fpc', d['frames_per_call'], d['covered_pixels'], d['checksum'], 'timeouts', d['signal_timeouts'], 'speedup', d.get('speedup_vs_single_gpu'), d['nvlink_bytes_per_frame'], d.get('single_gpu_same_calls'))
+P

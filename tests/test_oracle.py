@@ -209,3 +209,87 @@ def test_oracle_against_reference_c_prototype(oracle):
     assert np.array_equal(got[:2500].view(np.uint32), want[:2500].view(np.uint32))
     scale = np.abs(m).max() * np.abs(v).max(axis=1, keepdims=True)
     assert (np.abs(got - want) <= 4 * np.finfo(np.float32).eps * scale).all()
+
+
+def test_go_reference_pin_if_present(oracle):
+    """tests/golden/go_reference_outputs.json is written by scripts/compare_go_dump.py --pin from a run of the UNMODIFIED Go
+    reference (go/parity/parity_dump.go).  It does not exist until somebody with a Go toolchain has produced it: until
+    then parity stays "unpinned"  and this test has nothing to check."""
+    import hashlib
+    import json
+    import os
+
+    import scene_defs
+    from gorender_b200 import workloads
+
+    path = os.path.join(workloads.GOLDEN_DIR, "go_reference_outputs.json")
+    if not os.path.exists(path):
+        pytest.skip("no output of the Go reference has been committed yet")
+    ref = json.load(open(path))
+    assert ref, "empty pin"
+    for name, gref in ref.items():
+        sc = scene_defs.PINNED[name]()
+        res = oracle.draw(sc.renderer(None), sc.objects, sc.camera)
+        assert res["tpf"] == gref["tpf"], name
+        assert hashlib.sha256(res["pixels"].tobytes()).hexdigest() == gref["pixels_sha256"], name
+        assert hashlib.sha256(res["zbuffer"].tobytes()).hexdigest() == gref["zbuffer_sha256"], name
+
+
+def test_go_harness_scene_export_round_trips(oracle, tmp_path):
+    """The scene files handed to the Go harness carry exactly what the oracle is fed: read back with the byte layout
+    go/parity/parity_dump.go's loadMesh uses, rebuilt with NewMesh and rendered, they give the same frames."""
+    import json
+    import struct
+    import subprocess
+    import sys
+
+    import gorender_b200 as g
+    import scene_defs
+
+    names = ["c2_cube_poseB", "multi_object", "fog_wire_gouraud", "c1_serial_tiles1"]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "scripts", "export_go_scenes.py"), str(tmp_path)] + names, check=True,
+                   capture_output=True)
+    scenes = json.load(open(tmp_path / "scenes.json"))
+    assert [s["name"] for s in scenes] == names
+
+    def load_mesh(fn):
+        b = open(tmp_path / fn, "rb").read()
+        nv, nvn, nf, ntex = struct.unpack_from("<4i", b, 0)
+        off = 16
+
+        def take(dtype, count, shape):
+            nonlocal off
+            a = np.frombuffer(b, dtype, count, off).reshape(shape).copy()
+            off += a.nbytes
+            return a
+
+        verts, vns = take("<f4", nv * 4, (nv, 4)), take("<f4", nvn * 4, (nvn, 4))
+        vidx, nidx = take("<i4", nf * 3, (nf, 3)), take("<i4", nf * 3, (nf, 3))
+        uvs, tidx = take("<f4", nf * 6, (nf, 3, 2)), take("<i4", nf, (nf,))
+        texs = []
+        for _ in range(ntex):
+            typ, w, h, scale, c0, c1, c2, c3 = struct.unpack_from("<3if4B", b, off)
+            off += 20
+            px = None
+            if typ != g.TextureTypeSolidColor:
+                px = take(np.uint8, w * h * 4, (h, w, 4))
+            texs.append(g.Texture(typ, (c0, c1, c2, c3), px, scale))
+        assert off == len(b)
+        return g.NewMesh(verts, vns if nvn else None, g.FaceArray(vidx, nidx, uvs, tidx, texs))
+
+    for s in scenes:
+        want_sc = scene_defs.PINNED[s["name"]]()
+        objs = []
+        meshes = [load_mesh(fn) for fn in s["meshes"]]
+        for so in s["objects"]:
+            o = g.NewObject(meshes[so["mesh"]])
+            o.Translation, o.Rotation, o.Scale = (np.array(so[k], np.float32) for k in ("translation", "rotation", "scale"))
+            objs.append(o)
+        cam = g.Camera(s["camera"]["position"], s["camera"]["direction"], s["camera"]["up"])
+        r = scene_defs.SceneDef(s["width"], s["height"], objs, cam, {k: v for k, v in s["options"].items()}, parallel=s["num_tiles"] == 16).renderer(None)
+        r.FogStart, r.FogEnd, r.FogColor = np.float32(s["fog_start"]), np.float32(s["fog_end"]), tuple(s["fog_color"])
+        got = oracle.draw(r, objs, cam)
+        want = oracle.draw(want_sc.renderer(None), want_sc.objects, want_sc.camera)
+        assert got["tpf"] == want["tpf"], s["name"]
+        assert np.array_equal(got["pixels"], want["pixels"]) and np.array_equal(got["zbuffer"].view(np.uint32), want["zbuffer"].view(np.uint32)), s["name"]
