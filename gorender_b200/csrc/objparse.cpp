@@ -170,8 +170,13 @@ bool scan_int(const char *&p, const char *e, long &v) {
     bool neg = false;
     if (q < e && (*q == '+' || *q == '-')) neg = *q++ == '-';
     if (q >= e || *q < '0' || *q > '9') return false;
+    // Go's Sscanf("%d") into an int fails with "value out of range" beyond int64; an OBJ index that large cannot refer
+    // to anything anyway, so saturate well inside `long` (no signed overflow) and let the range checks reject it
     long x = 0;
-    while (q < e && *q >= '0' && *q <= '9') x = x * 10 + (*q++ - '0');
+    while (q < e && *q >= '0' && *q <= '9') {
+        if (x < (1L << 52)) x = x * 10 + (*q - '0');
+        q++;
+    }
     v = neg ? -x : x;
     p = q;
     return true;
@@ -304,8 +309,11 @@ std::string parse_face(Span line, const Segment &sg, const float *tv, int32_t *v
             uvs[2 * k + 1] = tv[2 * (sg.vt0 + (size_t)idx) + 1];
         }
     for (int k = 0; k < 3; k++) {
-        vidx[k] = (int32_t)(v[k] - vOff - 1);
-        nidx[k] = (int32_t)vn[k];
+        // the indices are checked against the mesh when it is uploaded (the reference panics on use, renderer.go:318-330):
+        // keep anything that does not fit the ABI's int32 out of range instead of letting it wrap into a valid index
+        const long vi = v[k] - vOff - 1, ni = vn[k];
+        vidx[k] = (vi < INT32_MIN || vi > INT32_MAX) ? INT32_MAX : (int32_t)vi;
+        nidx[k] = (ni < INT32_MIN || ni > INT32_MAX) ? INT32_MAX : (int32_t)ni;
     }
     return "";
 }

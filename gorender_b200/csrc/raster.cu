@@ -171,6 +171,9 @@ __device__ __forceinline__ void fine_stage(const WarpTris &wt, const uint32_t *r
             if (key > *(volatile unsigned long long *)p) atomicMax(p, key);
         }
     }
+    // the ring entries just read are rewritten by the pushes that follow (compute-sanitizer racecheck flags the
+    // read-then-write of different lanes without it)
+    __syncwarp();
 }
 
 // Raster bbox from the second 16 bytes of a record.

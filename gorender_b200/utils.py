@@ -2,5 +2,5 @@
 
 
 def isPowerOfTwo(n: int) -> bool:
-    """utils.go:5-7."""
-    return (n & (n - 1)) == 0
+    """utils.go:7-9."""
+    return n != 0 and (n & (n - 1)) == 0

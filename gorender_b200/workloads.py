@@ -14,6 +14,10 @@ from .mesh import FaceArray, Mesh, NewMesh, NewObject, Object
 from .renderer import Camera
 from .texture import NewImageTexture, Texture, TextureTypeSolidColor
 
+# the reference's two model files (models/suzanne.obj, models/cube.obj + textures-16.png) as LoadObjFile left them,
+# carried as package data so that the workloads do not depend on /root/reference or on the test tree
+ASSETS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+# the oracle's pinned outputs live with the tests
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
@@ -45,11 +49,11 @@ def load_mesh_fixture(path: str) -> Mesh:
 
 
 def suzanne() -> Mesh:
-    return load_mesh_fixture(os.path.join(GOLDEN_DIR, "suzanne.npz"))
+    return load_mesh_fixture(os.path.join(ASSETS_DIR, "suzanne.npz"))
 
 
 def cube() -> Mesh:
-    return load_mesh_fixture(os.path.join(GOLDEN_DIR, "cube.npz"))
+    return load_mesh_fixture(os.path.join(ASSETS_DIR, "cube.npz"))
 
 
 def checker_texture(size: int = 64, cells: int = 8) -> Texture:

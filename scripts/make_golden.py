@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/ from the reference's model files (run in the
+"""Regenerates gorender_b200/assets/ and tests/golden/ from the reference's model files (run in the
 build container, where /root/reference exists; the GPU box only sees the
 committed outputs).
 
@@ -29,10 +29,11 @@ REF = "/root/reference/models"
 
 def main():
     os.makedirs(workloads.GOLDEN_DIR, exist_ok=True)
+    os.makedirs(workloads.ASSETS_DIR, exist_ok=True)
     if os.path.isdir(REF):
         for name in ("suzanne", "cube"):
             mesh = g.LoadMeshFile(os.path.join(REF, name + ".obj"), False)[0]
-            workloads.save_mesh_fixture(os.path.join(workloads.GOLDEN_DIR, name + ".npz"), mesh)
+            workloads.save_mesh_fixture(os.path.join(workloads.ASSETS_DIR, name + ".npz"), mesh)
             print("wrote", name + ".npz", mesh.Vertices.shape, len(mesh.Faces))
     else:
         print("no /root/reference: keeping the committed mesh fixtures")

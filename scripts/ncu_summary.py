@@ -28,7 +28,8 @@ def to_bytes(r, name):
 kernels = {}
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
-    key = "setup" if "setup_kernel" in name else "raster" if "raster_kernel" in name else None
+    key = ("setup" if ("setup_kernel" in name or "setup_list_kernel" in name) else "raster" if "raster_kernel" in name
+           else "mirror" if "mirror_update_kernel" in name else "reject" if "reject_kernel" in name else None)
     if key is None or key in kernels:
         continue
     rd, wr = to_bytes(r, "dram__bytes_read.sum"), to_bytes(r, "dram__bytes_write.sum")
@@ -47,6 +48,7 @@ for r in rows[2:]:
         "fp32_pipe_fma_pct": f(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
         "l1_hit_pct": f(r, "l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": f(r, "lts__t_sector_hit_rate.pct"),
     }
-json.dump({"source": "ncu --set full --clock-control none, scripts/kernel_times.py c3 (C3 scene, one batched draw of "
-                     f"{frames} frames), B200", "kernels": kernels}, open(out, "w"), indent=1)
+what = sys.argv[4] if len(sys.argv) > 4 else "scripts/kernel_times.py c3 (C3 scene)"
+json.dump({"source": f"ncu --set full --clock-control none, {what}, one batched draw of {frames} frames, B200", "kernels": kernels},
+          open(out, "w"), indent=1)
 print(json.dumps(kernels, indent=1))

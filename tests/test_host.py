@@ -74,7 +74,7 @@ def test_obj_loader_on_reference_models():
     assert cube.Faces.UVs[0, 0].tolist() == [np.float32(0.062641), np.float32(0.499954)]
     # the committed fixtures are exactly what the loader produces
     for name, mesh in (("suzanne", suz[0]), ("cube", cube)):
-        fx = workloads.load_mesh_fixture(os.path.join(workloads.GOLDEN_DIR, name + ".npz"))
+        fx = workloads.load_mesh_fixture(os.path.join(workloads.ASSETS_DIR, name + ".npz"))
         assert np.array_equal(bits(fx.Vertices), bits(mesh.Vertices))
         assert np.array_equal(fx.Faces.VertexIndices, mesh.Faces.VertexIndices)
         assert np.array_equal(bits(fx.Faces.UVs), bits(mesh.Faces.UVs))
