@@ -69,10 +69,24 @@ def NewImageTexture(img) -> Texture:
     return Texture(typ, pixels=premultiply_nrgba(rgba), scale=1.0)
 
 
-def LoadTextureFile(filename: str) -> Texture:
-    """texture.go:91-103 (PNG/JPEG decode via PIL instead of Go's image/*)."""
+def LoadTextureFile(filename: str, strict: bool = False) -> Texture:
+    """texture.go:91-103 (decode via PIL instead of Go's image/*).
+
+    Texel parity with the reference holds for what PIL and Go decode identically: 8-bit greyscale / RGB / RGBA PNGs
+    (the reference's own `models/textures-16.png` is one).  JPEG (Go's image/jpeg uses another IDCT and YCbCr -> RGB
+    conversion), 16-bit PNGs (Go narrows after the premultiply, PIL before) and paletted PNGs with transparency can
+    differ by a few codes; they load with a warning, or raise with `strict=True`."""
+    import warnings
+
     from PIL import Image
 
     with Image.open(filename) as im:
         im.load()
+        exact = im.format == "PNG" and im.mode in ("L", "LA", "RGB", "RGBA")
+        if not exact:
+            msg = (f"{filename}: {im.format} / mode {im.mode} is outside the decode domain in which texels are identical to "
+                   "the Go reference's (8-bit L / LA / RGB / RGBA PNG)")
+            if strict:
+                raise ValueError(msg)
+            warnings.warn(msg)
         return NewImageTexture(im)
