@@ -4,7 +4,10 @@ mode "gloo": CPU, host-side logic only — every rank produces its strip of a fr
   oracle, strips are gathered to rank 0 with the product's gather_strips_to_rank0 and compared
   with the whole-frame oracle render; pose blocks are checked to tile the batch.
 mode "nccl": GPU — the same through the CUDA path (strip draws into torch-owned framebuffers,
-  NCCL gather over NVLink), plus a frame-parallel batch compared per rank with the oracle.
+  NCCL gather over NVLink), the strip group (rank 0's framebuffers shared over CUDA IPC, tiles pushed over
+  NVLink, device-side hand-off flags), plus a frame-parallel batch compared per rank with the oracle.
+mode "ipc1": the strip group with every rank on GPU 0 (CUDA IPC works between processes on one device; the
+  process group is gloo, which only carries the handles and the barriers) — what a one-GPU box can run.
 """
 import os
 import sys
@@ -63,29 +66,37 @@ def main():
         print(f"rank {rank} ok")
         return
 
+    one_gpu = mode == "ipc1"
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if one_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
     dev = g.Device(local, stream.cuda_stream)
     with torch.cuda.stream(stream):
-        # ---- sort-first strips, gathered to rank 0 over NCCL
-        tfb = parallel.TorchFrameBuffer(W, H, 1, dev, torch.device("cuda", local))
-        tfb.color.zero_()
-        tfb.depth.zero_()
-        r = sc.renderer(tfb.fb)
-        packed = r.pack_objects(sc.objects, [sc.camera])
-        parallel.draw_strip(r, packed, H, world, rank)
-        parallel.gather_strips_to_rank0(tfb.color[0], tfb.depth[0], H)
-        stream.synchronize()
-        if rank == 0:
-            ref = orc.draw(r, sc.objects, sc.camera)
-            assert np.array_equal(tfb.color[0].cpu().numpy(), ref["pixels"]), "gathered colour differs"
-            assert np.array_equal(tfb.depth[0].cpu().numpy().view(np.uint32), ref["zbuffer"].view(np.uint32))
+        if not one_gpu:
+            # ---- sort-first strips, gathered to rank 0 over NCCL
+            tfb = parallel.TorchFrameBuffer(W, H, 1, dev, torch.device("cuda", local))
+            tfb.color.zero_()
+            tfb.depth.zero_()
+            r = sc.renderer(tfb.fb)
+            packed = r.pack_objects(sc.objects, [sc.camera])
+            parallel.draw_strip(r, packed, H, world, rank)
+            parallel.gather_strips_to_rank0(tfb.color[0], tfb.depth[0], H)
+            stream.synchronize()
+            if rank == 0:
+                ref = orc.draw(r, sc.objects, sc.camera)
+                assert np.array_equal(tfb.color[0].cpu().numpy(), ref["pixels"]), "gathered colour differs"
+                assert np.array_equal(tfb.depth[0].cpu().numpy().view(np.uint32), ref["zbuffer"].view(np.uint32))
         # ---- sort-first strips the B200 way: rank 0's framebuffers shared over CUDA IPC, every rank's raster kernel
         #      writes its rows into them over NVLink, device-side flags hand the frame over; strips balanced by the
         #      busy tiles of a probe frame; double-buffered; rank 0 mirrors each frame into host memory
         probe = g.FrameBuffer(W, H, 1, dev)
         pr = sc.renderer(probe)
+        packed = pr.pack_objects(sc.objects, [sc.camera])
         pr.draw_packed(packed, 0)
         weights = probe.tile_flags(0).sum(axis=1)
         rows = parallel.balanced_strip_rows(weights, world, H)
@@ -104,7 +115,7 @@ def main():
         for f in range(5):
             k = f & 1
             grp.draw(k, frames[f])
-            tpf = torch.tensor([int(0)], dtype=torch.int64, device="cuda")
+            tpf = torch.tensor([int(0)], dtype=torch.int64, device="cpu" if one_gpu else "cuda")
             if rank == 0:
                 fbk = grp.fbs[k]
                 fbk.update_mirrors_async(0, 1, fbk.mirror("Pixels"), fbk.mirror("ZBuffer"))   # reads the whole frame, after every rank's flag
@@ -130,6 +141,11 @@ def main():
             o.Translation = b0
         grp.close()
         probe.close()
+        if one_gpu:
+            dist.barrier()
+            dist.destroy_process_group()
+            print(f"rank {rank} ok")
+            return
         # ---- frame-parallel: each rank renders its block of poses
         objs, cams = workloads.config_c5(n=16, poses=10)
         b, e = parallel.pose_block(len(cams), world, rank)

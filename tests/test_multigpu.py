@@ -32,6 +32,15 @@ def test_strip_gather_and_pose_blocks_gloo(world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_strip_group_over_cuda_ipc_on_one_gpu(world):
+    """The sort-first exchange step — rank 0's framebuffers shared over CUDA IPC, every other rank pushing its busy tiles
+    into them, device-side hand-off flags, two buffers in flight, rank 0 mirroring each frame into host memory — with all
+    ranks on GPU 0, so that a one-GPU box runs it too (frames compared with the oracle, TPFs summed over ranks)."""
+    _launch("ipc1", world)
+
+
+@pytest.mark.gpu
 def test_strips_and_frame_parallel_nccl():
     import torch
 
