@@ -23,43 +23,55 @@
 
 namespace gr {
 
-// A small fixed grid walks the (frame, tile) pairs; thread t owns the 4 pixels (4 * (t & 7) .., t >> 3) of the
-// tile, like the raster kernel's write-back, so both planes move as 128-bit accesses.  The grid is kept small on
-// purpose: the kernel is bound by PCIe (or NVLink), runs on the high-priority copy stream beside the render
-// kernels of the next batch, and one block per tile would fill every SM's thread slots with blocks that do
-// nothing but wait for the bus — the update would then serialise with rendering instead of hiding behind it.
+// A small fixed grid walks the frames' tile rows in groups of 4 horizontally adjacent tiles (128 pixels): lane l of a
+// warp owns the 4 pixels 4l .. 4l+3 of a row of the group, so that a warp's stores are one contiguous 512-byte run when
+// neighbouring tiles are written together — the usual case inside an object — instead of four separate 128-byte tile rows
+// (measured on the box, scripts/probes/pcie_probe.cu: 52 GB/s against 46.7 GB/s over PCIe; both planes move as 128-bit
+// accesses).  Lanes of tiles that are skipped are predicated off.  The grid is kept small on purpose: the kernel is
+// bound by PCIe (or NVLink), runs on the high-priority copy stream beside the render kernels of the next batch, and
+// one block per tile would fill every SM's thread slots with blocks that do nothing but wait for the bus — the update
+// would then serialise with rendering instead of hiding behind it.
 constexpr int kMirrorBlocksPerSM = 3;   // measured 1..16 on C3 beside rendering (scripts/mirror_tune.py): 3 is best by a few per cent
+constexpr int kGroupTiles = 4;
 
 __global__ void __launch_bounds__(256) mirror_update_kernel(const MirrorArgs m, const int nframes) {
-    const int nTiles = m.ntx * m.nty, perFrame = m.ntx * m.tileRows;
+    const int nTiles = m.ntx * m.nty;
+    const int groupsX = (m.ntx + kGroupTiles - 1) / kGroupTiles, perFrame = groupsX * m.tileRows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int idx = blockIdx.x; idx < nframes * perFrame; idx += gridDim.x) {
-        const int frame = idx / perFrame, tile = idx - frame * perFrame + m.tileRow0 * m.ntx;
-        const uint8_t busy = m.full ? 1 : m.tileBusy[(size_t)frame * nTiles + tile];
-        uint8_t *dirtyC = m.dirtyColor ? m.dirtyColor + (size_t)frame * nTiles + tile : nullptr;
-        uint8_t *dirtyZ = m.dirtyDepth ? m.dirtyDepth + (size_t)frame * nTiles + tile : nullptr;
-        const bool doC = dirtyC && (busy | *dirtyC);
-        const bool doZ = dirtyZ && (busy | *dirtyZ);
-        if (!doC && !doZ) continue;   // block-uniform: the mirror's tile is background and stays background
-        const int tx = tile % m.ntx, ty = tile / m.ntx;
-        const int gx = tx * kTile + (threadIdx.x & 7) * 4, gy = ty * kTile + (threadIdx.x >> 3);
-        if (gy < m.height && gx < m.width) {
-            const size_t pix = ((size_t)frame * m.height + gy) * m.width + gx;
-            if ((m.width & 3) == 0) {
-                if (doC) *reinterpret_cast<uint4 *>(m.hostColor + pix) = *reinterpret_cast<const uint4 *>(m.color + pix);
-                if (doZ) *reinterpret_cast<float4 *>(m.hostDepth + pix) = *reinterpret_cast<const float4 *>(m.depth + pix);
-            } else {
-                for (int k = 0; k < 4 && gx + k < m.width; k++) {
-                    if (doC) m.hostColor[pix + k] = m.color[pix + k];
-                    if (doZ) m.hostDepth[pix + k] = m.depth[pix + k];
+        const int frame = idx / perFrame, g = idx - frame * perFrame;
+        const int ty = m.tileRow0 + g / groupsX, tx = (g % groupsX) * kGroupTiles + (lane >> 3);   // this lane's tile
+        const bool inRow = tx < m.ntx;
+        const size_t flag = (size_t)frame * nTiles + (size_t)ty * m.ntx + tx;
+        const uint8_t busy = !inRow ? 0 : (m.full ? 1 : m.tileBusy[flag]);
+        const bool doC = inRow && m.dirtyColor && (busy | m.dirtyColor[flag]);
+        const bool doZ = inRow && m.dirtyDepth && (busy | m.dirtyDepth[flag]);
+        // block-uniform: every tile of the group is background in the mirror and stays background
+        if (!__syncthreads_or(doC || doZ)) continue;
+        const int gx = tx * kTile + (lane & 7) * 4;
+        if (gx < m.width && (doC || doZ)) {
+#pragma unroll
+            for (int r = 0; r < kTile / 8; r++) {
+                const int gy = ty * kTile + warp + 8 * r;
+                if (gy >= m.height) break;
+                const size_t pix = ((size_t)frame * m.height + gy) * m.width + gx;
+                if ((m.width & 3) == 0) {
+                    if (doC) *reinterpret_cast<uint4 *>(m.hostColor + pix) = *reinterpret_cast<const uint4 *>(m.color + pix);
+                    if (doZ) *reinterpret_cast<float4 *>(m.hostDepth + pix) = *reinterpret_cast<const float4 *>(m.depth + pix);
+                } else {
+                    for (int k = 0; k < 4 && gx + k < m.width; k++) {
+                        if (doC) m.hostColor[pix + k] = m.color[pix + k];
+                        if (doZ) m.hostDepth[pix + k] = m.depth[pix + k];
+                    }
                 }
             }
         }
-        __syncthreads();   // every warp has read the flags (the skip above is block-uniform)
-        if (threadIdx.x == 0) {
-            // nobody else touches this tile's flags in this launch
-            if (doC) *dirtyC = busy;
-            if (doZ) *dirtyZ = busy;
-            if (m.targetBusy) m.targetBusy[(size_t)frame * nTiles + tile] = busy;
+        __syncthreads();   // every warp has read the flags of the group's tiles
+        if (warp == 0 && (lane & 7) == 0 && (doC || doZ)) {
+            // one lane per tile; nobody else touches these flags in this launch
+            if (doC) m.dirtyColor[flag] = busy;
+            if (doZ) m.dirtyDepth[flag] = busy;
+            if (m.targetBusy) m.targetBusy[flag] = busy;
             if (m.tilesWritten) atomicAdd(m.tilesWritten, (unsigned long long)((doC ? 1 : 0) + (doZ ? 1 : 0)));
         }
     }
@@ -73,7 +85,7 @@ void launch_mirror_update(const MirrorArgs &m, int nframes, cudaStream_t s) {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    const long long total = (long long)nframes * m.ntx * m.tileRows;
+    const long long total = (long long)nframes * ((m.ntx + kGroupTiles - 1) / kGroupTiles) * m.tileRows;
     static const int perSM = [] {   // tuning knob (scripts/mirror_tune.py)
         const char *e = getenv("GRB_MIRROR_BLOCKS_PER_SM");
         const int v = e ? atoi(e) : 0;

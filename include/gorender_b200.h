@@ -291,7 +291,8 @@ typedef struct grb_mirror grb_mirror;
 int32_t grb_mirror_create(grb_context *ctx, int32_t width, int32_t height, int32_t frames, int32_t plane,
                           void *host_plane, grb_mirror **out);
 /* A mirror whose plane is a plane of `target` (normally a framebuffer opened with grb_framebuffer_ipc_open):
- * updating it pushes tiles into that framebuffer, and keeps its per-tile background flags in step. */
+ * updating it pushes tiles into that framebuffer, and keeps its per-tile background flags in step.  Destroy the
+ * mirror before `target`. */
 int32_t grb_mirror_create_on_framebuffer(grb_context *ctx, grb_framebuffer *target, int32_t plane, grb_mirror **out);
 int32_t grb_mirror_destroy(grb_mirror *m);
 int32_t grb_mirror_invalidate(grb_mirror *m);

@@ -23,6 +23,23 @@ __global__ void __launch_bounds__(256) scatter_tiles(const uint4 *__restrict__ s
     dstC[i] = srcC[i];
     dstZ[i] = srcZ[i];
 }
+// variant: a block takes a group of 4 horizontally adjacent tiles (all assumed busy) and every warp writes whole 512-byte
+// rows of the group, so that the stores of a warp are contiguous over 4 tiles instead of 4 separate 128-byte tile rows
+__global__ void __launch_bounds__(256) scatter_groups(const uint4 *__restrict__ srcC, const uint4 *__restrict__ srcZ, uint4 *dstC, uint4 *dstZ,
+                               const int *groups, int ng, int W, int H, int ntx, size_t framePix4) {
+    const int g = groups[blockIdx.x], f = blockIdx.y;          // group index: tile (tx0 = 4 * (g % (ntx/4)), ty)
+    const int gx4 = ntx / 4;
+    const int tx0 = (g % gx4) * 4, ty = g / gx4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < 32; r += 8) {
+        const int gy = ty * 32 + r;
+        if (gy >= H) break;
+        const size_t i = (size_t)f * framePix4 + ((size_t)gy * W) / 4 + tx0 * 8 + lane;
+        dstC[i] = srcC[i];
+        dstZ[i] = srcZ[i];
+    }
+}
+
 __global__ void __launch_bounds__(256) compact_tiles(const uint4 *__restrict__ srcC, const uint4 *__restrict__ srcZ, uint4 *out,
                               const int *tiles, int nt, int W, int H, int ntx, size_t framePix4) {
     const int t = tiles[blockIdx.x], f = blockIdx.y;
@@ -80,6 +97,24 @@ int main(int argc, char **argv) {
         timeit(name, bytes, [&] { scatter_tiles<<<dim3(nt, F), 256, 0, s>>>(dC, dZ, hC, hZ, dT, nt, W, H, ntx, pix / 4); });
         snprintf(name, sizeof name, "(b1) zero-copy scatter %d tiles x 1 frame", nt);
         timeit(name, bytes / F, [&] { scatter_tiles<<<dim3(nt, 1), 256, 0, s>>>(dC, dZ, hC, hZ, dT, nt, W, H, ntx, pix / 4); });
+        {   // (b2) the same tiles as groups of 4 adjacent ones (rounded down to whole groups)
+            std::vector<int> groups;
+            std::vector<char> isBusy(ntx * nty, 0);
+            for (int t : tiles) isBusy[t] = 1;
+            for (int ty = 0; ty < nty; ty++)
+                for (int gxi = 0; gxi < ntx / 4; gxi++) {
+                    bool all = true;
+                    for (int k = 0; k < 4; k++) all = all && isBusy[ty * ntx + gxi * 4 + k];
+                    if (all) groups.push_back(ty * (ntx / 4) + gxi);
+                }
+            if (!groups.empty()) {
+                int *dG; CK(cudaMalloc(&dG, groups.size() * 4)); CK(cudaMemcpy(dG, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice));
+                snprintf(name, sizeof name, "(b2) zero-copy, %zu groups of 4 tiles (512 B rows) x %d frames", groups.size(), F);
+                const int ng = (int)groups.size();
+                timeit(name, (double)ng * 4 * 8192 * F, [&] { scatter_groups<<<dim3(ng, F), 256, 0, s>>>(dC, dZ, hC, hZ, dG, ng, W, H, ntx, pix / 4); });
+                cudaFree(dG);
+            }
+        }
         CK(cudaMalloc(&dOut, (size_t)nt * 8192 * F)); CK(cudaHostAlloc(&hOut, (size_t)nt * 8192 * F, cudaHostAllocDefault));
         snprintf(name, sizeof name, "(c) compact + DMA %d tiles x %d frames (no host scatter)", nt, F);
         timeit(name, bytes, [&] {

@@ -255,3 +255,42 @@ def test_setup_without_raster_does_not_poison_the_next_draw(device, oracle):
     r.Draw(objs, cam)
     ref = oracle.draw(r, objs, cam)
     assert np.array_equal(fb.Pixels, ref["pixels"]) and np.array_equal(fb.ZBuffer.view(np.uint32), ref["zbuffer"].view(np.uint32))
+
+
+def test_mirror_errors_are_loud(device):
+    """Wrong plane type, wrong size, frame ranges, misaligned rows, signals on a framebuffer that is not shared: error codes
+    with messages, never a silent wrong copy."""
+    Err = g.renderer._cabi.GorenderError
+    fb = g.FrameBuffer(320, 256, 2, device)
+    mc = Mirror(device, 320, 256, 2, _cabi.GRB_PLANE_COLOR)
+    mz = Mirror(device, 320, 256, 2, _cabi.GRB_PLANE_DEPTH)
+    small = Mirror(device, 160, 128, 1, _cabi.GRB_PLANE_COLOR)
+    with pytest.raises(Err, match="plane"):
+        fb.update_mirrors_async(0, 1, mz, None)                 # a depth mirror in the colour slot
+    with pytest.raises(Err, match="sizes differ"):
+        fb.update_mirrors_async(0, 1, small, None)
+    with pytest.raises(Err, match="outside the mirror"):
+        fb.update_mirrors_async(0, 2, mc, mz, color_frame0=1)
+    with pytest.raises(Err, match="outside the framebuffer"):
+        fb.update_mirrors_async(1, 2, mc, mz)
+    with pytest.raises(Err, match="tile-aligned"):
+        fb.update_mirrors_async(0, 1, mc, mz, rows=(5, 64))
+    with pytest.raises(Err, match="not shared"):
+        fb.signal(0, 1)
+    with pytest.raises(Err, match="not shared"):
+        fb.wait_signals(0, 1, 1)
+    other = g.Device(0)
+    try:
+        with pytest.raises(Err, match="another context"):
+            other.check(other.lib.grb_mirror_update_async(other.h, fb.handle, 0, 1, mc.h, 0, None, 0))
+    finally:
+        other.close()
+    # and the valid call still works afterwards
+    objs, cam = workloads.config_c1()
+    r = g.Renderer(fb)
+    r.draw_packed(r.pack_objects(objs, [cam, cam]), 0, sync=False)
+    fb.update_mirrors_async(0, 2, mc, mz, rows=(0, 256))
+    mc.wait()
+    mz.wait()
+    px, z = fb.read(0, 2)
+    assert np.array_equal(mc.array, px) and np.array_equal(mz.array.view(np.uint32), z.view(np.uint32))
