@@ -539,10 +539,10 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     const int tile = ty * a.ntx + tx;
     const int tileX = tx * kTile, tileY = ty * kTile;
 
-    uint32_t *descCount = a.descCount + (size_t)frame * nTiles + tile;
+    const size_t frameTile = (size_t)frame * nTiles + tile;
+    uint32_t *descCount = a.descCount + frameTile;
     const uint32_t nDescAll = *descCount;
     const uint32_t nBig = a.counters[frame].bigCount;
-    const uint32_t nOverflow = nDescAll > a.descCap ? min(a.counters[frame].overflowCount, a.overflowCap) : 0u;
 
     const int gx = tileX + px, gy = tileY + py;
     const bool inImage = gy < a.height && gx < a.width;
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     }
     // host mirrors and strip pushes (present.cu) skip tiles that hold nothing but the cleared background; with
     // overlays or post passes any tile may differ from it
-    if (tid == 0 && a.tileBusy != nullptr) a.tileBusy[(size_t)frame * nTiles + tile] = (POST || !empty) ? 1 : 0;
+    if (tid == 0 && a.tileBusy != nullptr) a.tileBusy[frameTile] = (POST || !empty) ? 1 : 0;
     // ---- cleared background straight to HBM
     if (empty) {
         if (inImage) {
@@ -588,6 +588,8 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     const PackedRec *rec = a.rec + (size_t)frame * a.recCap;
     const TileDesc *desc = a.desc + ((size_t)frame * nTiles + tile) * a.descCap;
     const uint32_t nDesc = min(nDescAll, a.descCap);
+    // (only busy tiles get here: the 86 % of C3's tile blocks that are empty have returned above)
+    const uint32_t nOverflow = nDescAll > a.descCap ? min(a.counters[frame].overflowCount, a.overflowCap) : 0u;
 
     for (int i = tid; i < kTilePix; i += kRasterThreads) keys[i] = kBackgroundKey;
     if (tid < 2) largeCount[tid] = 0;
