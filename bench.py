@@ -508,7 +508,22 @@ def strips_leg(args, g, torch, dist, rank, world, local_rank, frames_timed=256, 
             def finish():
                 pass
         elif exchange == "peer":
-            grp = parallel.StripGroup(dev, W4, H4, nbuf=2, rows=rows, frames=fpc)
+            # if any rank cannot map rank 0's framebuffers (CUDA IPC refused by the platform), every rank leaves the leg together
+            grp, err = None, ""
+            try:
+                grp = parallel.StripGroup(dev, W4, H4, nbuf=2, rows=rows, frames=fpc)
+            except Exception as e:  # noqa: BLE001
+                err = f"{type(e).__name__}: {e}"
+            if dist is not None:
+                okt = torch.tensor([0 if grp is None else 1], device="cuda", dtype=torch.int32)
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                if int(okt[0]) == 0:
+                    if grp is not None:
+                        grp.close_local()
+                    dev.close()
+                    return {"error": "strip group could not be set up on every rank" + (": " + err if err else "")} if rank == 0 else None
+            elif grp is None:
+                raise RuntimeError(err)
 
             def one_frame(n):
                 k = n & 1
@@ -618,7 +633,9 @@ def run_strips(args, rank: int, world: int, local_rank: int):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     res = strips_leg(args, g, torch, dist, rank, world, local_rank, frames_timed=max(args.steps, 1) * 8, warm=max(args.warmup, 1) * 4)
-    if rank == 0:
+    if rank == 0 and "error" in res:
+        print(json.dumps(res), flush=True)
+    elif rank == 0:
         res.update({"steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_frame"] * 8, "higher_is_better": True,
                     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                     "config": {"workload": res["workload"], "frames_per_step": 8, "parallelism": f"sort-first strips x{world}"}})

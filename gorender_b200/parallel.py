@@ -152,6 +152,16 @@ class StripGroup:
             self.fbs[k].signal(self.CONSUMED_SLOT, self.uses[k])
             self.released[k] = self.uses[k]
 
+    def close_local(self) -> None:
+        """Not collective: drop this rank's handles (after a failed collective set-up)."""
+        self.dev.synchronize()
+        for mc, mz in self.push:
+            mc.close()
+            mz.close()
+        for fb in self.fbs + self.local:
+            fb.close()
+        self.fbs, self.local, self.push = [], [], []
+
     def close(self) -> None:
         """Collective: the other ranks unmap rank 0's memory before rank 0 frees it."""
         self.dev.synchronize()
