@@ -105,7 +105,9 @@ typedef struct grb_draw_params {
     int32_t ref_tiles;       /* the reference's numTiles: 16 (parallel) or 1; decides
                                 TPF and the tile-list membership rule (renderer.go:226-244) */
     int32_t row_begin;       /* sort-first strip: rasterise rows [row_begin,row_end); */
-    int32_t row_end;         /*   both multiples of GRB_TILE; 0,0 = whole frame       */
+    int32_t row_end;         /*   both multiples of GRB_TILE; 0,0 = whole frame.  Geometry that cannot reach the rows is
+                                skipped (object, then per 32 faces), and a triangle's TPF is counted by the strip that owns
+                                its top row: the TPFs of the strips of a frame add up to the frame's                      */
     float fog_start, fog_end;/* GRB_OPT_FOG: Fog(fogStart, fogEnd, c); renderer.go:479 has 0.100, 0.033 */
     uint8_t fog_color[4];    /*   ... and {100,100,100,255}                                */
 } grb_draw_params;

@@ -294,3 +294,33 @@ def test_mirror_errors_are_loud(device):
     mz.wait()
     px, z = fb.read(0, 2)
     assert np.array_equal(mc.array, px) and np.array_equal(mz.array.view(np.uint32), z.view(np.uint32))
+
+
+def test_mirror_of_wrapped_framebuffer_copies_everything(device):
+    """A framebuffer over caller-owned device memory (torch tensors) may be written behind the library's back: its tile flags
+    cannot be trusted, so a mirror update moves every tile."""
+    import torch
+
+    from gorender_b200.parallel import TorchFrameBuffer
+
+    tfb = TorchFrameBuffer(320, 256, 1, device, torch.device("cuda", 0))
+    tfb.color.zero_()
+    tfb.depth.zero_()
+    torch.cuda.synchronize()
+    mc = Mirror(device, 320, 256, 1, _cabi.GRB_PLANE_COLOR)
+    mz = Mirror(device, 320, 256, 1, _cabi.GRB_PLANE_DEPTH)
+    objs, cam = workloads.config_c1()
+    r = g.Renderer(tfb.fb)
+    r.draw_packed(r.pack_objects(objs, [cam]), 0)
+    tfb.fb.update_mirrors_async(0, 1, mc, mz)
+    mc.wait()
+    mz.wait()
+    assert np.array_equal(mc.array[0], tfb.color[0].cpu().numpy())
+    device.synchronize()
+    tfb.color[0, :8, :8] = 9                      # the owner scribbles into a background corner of its tensor
+    torch.cuda.synchronize()
+    tfb.fb.update_mirrors_async(0, 1, mc, mz)
+    mc.wait()
+    assert (mc.array[0, :8, :8] == 9).all()
+    w, full = mc.stats()
+    assert w == full                              # every tile, both times
