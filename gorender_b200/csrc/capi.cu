@@ -696,12 +696,12 @@ int32_t mirror_args(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32
     if (color) {
         m.hostColor = static_cast<uchar4 *>(color->devPtr) + (size_t)cf0 * npix;
         m.dirtyColor = color->dirty + (size_t)cf0 * nTiles;
-        m.tilesWritten = color->tilesWritten;
+        m.tilesWrittenColor = color->tilesWritten;
     }
     if (depth) {
         m.hostDepth = static_cast<float *>(depth->devPtr) + (size_t)df0 * npix;
         m.dirtyDepth = depth->dirty + (size_t)df0 * nTiles;
-        if (!m.tilesWritten) m.tilesWritten = depth->tilesWritten;
+        m.tilesWrittenDepth = depth->tilesWritten;
     }
     m.width = fb->width;
     m.height = fb->height;

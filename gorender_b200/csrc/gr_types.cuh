@@ -219,7 +219,7 @@ struct MirrorArgs {
     float *hostDepth;
     uint8_t *dirtyColor;        // [frames][nTiles] device flags: the host tile is not the cleared background
     uint8_t *dirtyDepth;
-    unsigned long long *tilesWritten;   // statistics (may be null)
+    unsigned long long *tilesWrittenColor, *tilesWrittenDepth;   // statistics, one counter per mirror (may be null)
     uint8_t *targetBusy;        // the mirror is another framebuffer (a strip pushed to its owner): that framebuffer's
                                 // own per-tile flags, kept in step so that ITS mirrors see these tiles (else null)
     int32_t width, height, ntx, nty;

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(256) mirror_update_kernel(const MirrorArgs m, 
             if (doC) m.dirtyColor[flag] = busy;
             if (doZ) m.dirtyDepth[flag] = busy;
             if (m.targetBusy) m.targetBusy[flag] = busy;
-            if (m.tilesWritten) atomicAdd(m.tilesWritten, (unsigned long long)((doC ? 1 : 0) + (doZ ? 1 : 0)));
+            if (doC && m.tilesWrittenColor) atomicAdd(m.tilesWrittenColor, 1ull);
+            if (doZ && m.tilesWrittenDepth) atomicAdd(m.tilesWrittenDepth, 1ull);
         }
     }
 }
