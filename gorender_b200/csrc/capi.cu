@@ -1584,6 +1584,20 @@ int32_t grb_draw_present(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, 
     }
     key.countersHost = ctx->hCounters;
     key.stageCapture = ctx->stageCapture ? 1 : 0;
+    // One whole frame with mirrors attached: the raster kernel's write-back stores the tiles into the host planes itself
+    // (MIRROR instantiation, raster.cu), so that a tile crosses PCIe while the others are still being rasterised; no
+    // separate mirror update follows.  (The rule is the mirrors' own; the kernel knows which tiles it leaves busy.)
+    const bool fused = key.hasMirror && nframes == 1 && key.job.a.tileRowBegin == 0 && key.job.a.tileRowEnd == key.job.a.nty &&
+                       key.m.targetBusy == nullptr;
+    if (fused) {
+        DrawArgs &a = key.job.a;
+        a.mirColor = key.m.hostColor;
+        a.mirDepth = key.m.hostDepth;
+        a.mirDirtyColor = key.m.dirtyColor;
+        a.mirDirtyDepth = key.m.dirtyDepth;
+        a.mirWrittenColor = key.m.tilesWrittenColor;
+        a.mirWrittenDepth = key.m.tilesWrittenDepth;
+    }
     cudaStream_t s = ctx->stream;
     if (fb->pendingRead) {  // a read-back / mirror update of these frames on the copy stream
         CK(ctx, cudaStreamWaitEvent(s, fb->readDone, 0));
@@ -1596,12 +1610,12 @@ int32_t grb_draw_present(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, 
         }
     auto enqueue_all = [&](bool capture) -> int32_t {
         if (int32_t r = enqueue_draw(ctx, key.job, capture)) return r;
-        if (key.hasMirror) launch_mirror_update(key.m, nframes, s);
+        if (key.hasMirror && !fused) launch_mirror_update(key.m, nframes, s);
         CK(ctx, cudaMemcpyAsync(ctx->hCounters, ctx->counters.p, (size_t)nframes * sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
         CK(ctx, cudaGetLastError());
         return GRB_OK;
     };
-    const int launches = launches_of(ctx, key.job) + (key.hasMirror ? 1 : 0);
+    const int launches = launches_of(ctx, key.job) + ((key.hasMirror && !fused) ? 1 : 0);
     const bool graphable = nframes == 1 && !ctx->timing;
     if (graphable) {
         GraphEntry *hit = nullptr;

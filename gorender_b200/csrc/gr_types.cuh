@@ -190,6 +190,13 @@ struct DrawArgs {
     uchar4 *color;              // [frames][H][W]
     float *depth;               // [frames][H][W]
     uint8_t *tileBusy;          // [frames][nTiles] 0: the tile holds the cleared background only (host mirrors skip it)
+    // One-frame draws with host mirrors attached (grb_draw_present): the raster kernel's write-back also stores the
+    // tile into the mirrors' host planes (MIRROR instantiation), so that the PCIe transfer of a tile overlaps the
+    // rasterisation of the others instead of following the whole frame.  Null: a separate mirror update follows.
+    uchar4 *mirColor;
+    float *mirDepth;
+    uint8_t *mirDirtyColor, *mirDirtyDepth;           // [nTiles] of the mirror frame written
+    unsigned long long *mirWrittenColor, *mirWrittenDepth;
     int32_t width, height;
     int32_t ntx, nty;           // device tiles
     int32_t tileRowBegin, tileRowEnd;  // strip, in tile rows

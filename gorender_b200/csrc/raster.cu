@@ -220,8 +220,9 @@ __device__ __forceinline__ uchar4 background(unsigned dots, int k) {
 }
 
 // Four consecutive pixels of one row: one 128-bit store each for colour and depth.
+// mirC / mirZ (MIRROR instantiation): also store the quad into the host mirrors' planes (frame 0 of the launch).
 __device__ __forceinline__ void write_quad(const DrawArgs &a, int frame, int gx, int gy, const uchar4 col[4],
-                                           const float zo[4]) {
+                                           const float zo[4], bool mirC = false, bool mirZ = false) {
     const size_t pix = ((size_t)frame * a.height + gy) * a.width + gx;
     if ((a.width & 3) == 0) {
         // gx is a multiple of 4 and so is width: 16-byte aligned, whole quad in range
@@ -230,10 +231,14 @@ __device__ __forceinline__ void write_quad(const DrawArgs &a, int frame, int gx,
         cq.z = *reinterpret_cast<const uint32_t *>(&col[2]); cq.w = *reinterpret_cast<const uint32_t *>(&col[3]);
         *reinterpret_cast<uint4 *>(a.color + pix) = cq;
         *reinterpret_cast<float4 *>(a.depth + pix) = make_float4(zo[0], zo[1], zo[2], zo[3]);
+        if (mirC) *reinterpret_cast<uint4 *>(a.mirColor + pix) = cq;
+        if (mirZ) *reinterpret_cast<float4 *>(a.mirDepth + pix) = make_float4(zo[0], zo[1], zo[2], zo[3]);
     } else {
         for (int k = 0; k < 4 && gx + k < a.width; k++) {
             a.color[pix + k] = col[k];
             a.depth[pix + k] = zo[k];
+            if (mirC) a.mirColor[pix + k] = col[k];
+            if (mirZ) a.mirDepth[pix + k] = zo[k];
         }
     }
 }
@@ -516,7 +521,9 @@ __device__ __forceinline__ void coop_pass(const uint32_t *largeQ, int nq, const 
 }
 
 // POST: the instantiation that also composes the overlays and runs the post passes (post_quad).
-template <bool POST>
+// MIRROR: one-frame draws with host mirrors attached — the write-back also goes to the mirrors' host planes, under the
+// mirrors' rule (present.cu): a tile is written iff it is busy now or was busy in the host copy.
+template <bool POST, bool MIRROR>
 __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_kernel(const __grid_constant__ DrawArgs a) {
     __shared__ unsigned long long keys[kTilePix];
     __shared__ WarpTris tris[kRasterThreads / 32];
@@ -564,6 +571,17 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
     // host mirrors and strip pushes (present.cu) skip tiles that hold nothing but the cleared background; with
     // overlays or post passes any tile may differ from it
     if (tid == 0 && a.tileBusy != nullptr) a.tileBusy[frameTile] = (POST || !empty) ? 1 : 0;
+    bool mirC = false, mirZ = false;
+    if constexpr (MIRROR) {   // (frame == 0: one-frame launches only)
+        const bool busy = POST || !empty;
+        mirC = a.mirColor != nullptr && (busy || a.mirDirtyColor[tile] != 0);
+        mirZ = a.mirDepth != nullptr && (busy || a.mirDirtyDepth[tile] != 0);
+        __syncthreads();      // every warp has read the host copy's flags before they are rewritten
+        if (tid == 0) {
+            if (mirC) { a.mirDirtyColor[tile] = busy ? 1 : 0; atomicAdd(a.mirWrittenColor, 1ull); }
+            if (mirZ) { a.mirDirtyDepth[tile] = busy ? 1 : 0; atomicAdd(a.mirWrittenDepth, 1ull); }
+        }
+    }
     // ---- cleared background straight to HBM
     if (empty) {
         if (inImage) {
@@ -579,7 +597,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                 const uint32_t none[4] = {0u, 0u, 0u, 0u};
                 post_quad(a, frame, gx, gy, col, zo, none);
             }
-            write_quad(a, frame, gx, gy, col, zo);
+            write_quad(a, frame, gx, gy, col, zo, mirC, mirZ);
         }
         return;
     }
@@ -765,7 +783,7 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
         zo[k] = z;
     }
     if constexpr (POST) post_quad(a, frame, gx, gy, col, zo, winner);
-    write_quad(a, frame, gx, gy, col, zo);
+    write_quad(a, frame, gx, gy, col, zo, mirC, mirZ);
     }
 }
 
@@ -778,15 +796,21 @@ void launch_raster(const DrawArgs &a, int nframes, cudaStream_t s) {
 #endif
     static const bool carveout = [] {
         if (GRB_CARVEOUT < 0) return false;
-        cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, GRB_CARVEOUT);
-        cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, GRB_CARVEOUT);
+        cudaFuncSetAttribute(raster_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, GRB_CARVEOUT);
+        cudaFuncSetAttribute(raster_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, GRB_CARVEOUT);
         return true;
     }();
     (void)carveout;
-    if (a.options & kOptPostPass)
-        raster_kernel<true><<<dim3(a.ntx, rows, nframes), kRasterThreads, 0, s>>>(a);
-    else
-        raster_kernel<false><<<dim3(a.ntx, rows, nframes), kRasterThreads, 0, s>>>(a);
+    const dim3 grid(a.ntx, rows, nframes);
+    const bool post = (a.options & kOptPostPass) != 0;
+    const bool mirror = nframes == 1 && (a.mirColor != nullptr || a.mirDepth != nullptr);
+    if (mirror) {
+        if (post) raster_kernel<true, true><<<grid, kRasterThreads, 0, s>>>(a);
+        else raster_kernel<false, true><<<grid, kRasterThreads, 0, s>>>(a);
+    } else {
+        if (post) raster_kernel<true, false><<<grid, kRasterThreads, 0, s>>>(a);
+        else raster_kernel<false, false><<<grid, kRasterThreads, 0, s>>>(a);
+    }
 }
 
 }  // namespace gr

@@ -316,8 +316,10 @@ int32_t grb_mirror_stats(grb_mirror *m, int64_t *tiles_written, int64_t *tiles_f
 /* The literal (*Renderer).Draw (renderer.go:443-483) for a caller whose FrameBuffer is host memory:
  * draw `nframes` frames, update the mirrors, return the stats — one call, one synchronisation.  A
  * one-frame call replays a CUDA graph of the whole sequence (matrix upload, counters, setup, raster,
- * mirror update, stats read-back) captured the first time this combination of scene, framebuffer,
- * options and mirrors is seen.  Mirrors and stats may be NULL. */
+ * stats read-back) captured the first time this combination of scene, framebuffer, options and mirrors
+ * is seen, and its raster kernel stores each tile it writes into the mirrors' host planes as well (same
+ * rule as a mirror update), so that tiles cross PCIe while the rest of the frame is still being
+ * rasterised.  Mirrors and stats may be NULL. */
 int32_t grb_draw_present(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, int32_t nframes,
                          const grb_object *objects, int32_t nobj, const grb_draw_params *params,
                          grb_mirror *color, int32_t color_frame0, grb_mirror *depth, int32_t depth_frame0,
