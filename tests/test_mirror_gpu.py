@@ -324,3 +324,21 @@ def test_mirror_of_wrapped_framebuffer_copies_everything(device):
     assert (mc.array[0, :8, :8] == 9).all()
     w, full = mc.stats()
     assert w == full                              # every tile, both times
+
+
+def test_signal_wait_times_out_instead_of_hanging(device):
+    """Device-side hand-off flags of a shared framebuffer: a wait nobody answers gives up after its timeout and is counted
+    (a dead peer must not hang the GPU); once the flag has been raised the same wait passes at once."""
+    fb = g.FrameBuffer(64, 64, 1, device)
+    fb.ipc_export()                                   # allocates the flag words (nobody opens the handle here)
+    before = device.signal_timeouts()
+    fb.wait_signals(5, 2, 1, timeout_ms=40)           # slots 5 and 6 are still 0
+    device.synchronize()
+    assert device.signal_timeouts() == before + 2     # one per unanswered slot
+    fb.signal(5, 3)
+    fb.signal(6, 1, on_copy_stream=True)
+    device.synchronize()
+    fb.wait_signals(5, 2, 1, timeout_ms=40)           # flags only grow: 3 >= 1 and 1 >= 1
+    device.synchronize()
+    assert device.signal_timeouts() == before + 2
+    fb.close()
