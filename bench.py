@@ -744,9 +744,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             else:
                 fbs_e[k].update_mirrors_async(0, B, mir_c[k], mir_z[k] if with_depth else None)
 
-    def time_e2e(steps, **kw):
+    def time_e2e(steps, count_tiles=False, **kw):
         step_e2e(0, **kw)
         barrier()
+        w0 = [m.stats() for m in mir_c + mir_z] if count_tiles else None     # (synchronises; outside the timed region)
         t0 = time.perf_counter()
         for s in range(W, W + steps):
             step_e2e(s, **kw)
@@ -754,6 +755,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             d.synchronize()
         sec = time.perf_counter() - t0
         barrier()
+        if count_tiles:
+            w1 = [m.stats() for m in mir_c + mir_z]
+            return sec / steps, sum(b[0] - a[0] for a, b in zip(w0, w1)), sum(b[1] - a[1] for a, b in zip(w0, w1))
         return sec / steps
 
     with torch.cuda.stream(stream):
@@ -761,13 +765,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         for m in mir_c + mir_z:
             m.invalidate()       # the DMA copies wrote the planes behind the mirrors' backs
         time_e2e(1)
-        w0 = [m.stats() for m in mir_c + mir_z]
-        e2e_sec = time_e2e(K)
-        w1 = [m.stats() for m in mir_c + mir_z]
+        e2e_sec, tiles_w, tiles_f = time_e2e(K, count_tiles=True)     # tiles written during the K timed steps only
         # colour only (what the reference's presenter consumes: Pixels2, main.go:297)
         e2e_px_sec = time_e2e(max(1, K // 2), with_depth=False)
-    tiles_w = sum(b[0] - a[0] for a, b in zip(w0, w1))
-    tiles_f = sum(b[1] - a[1] for a, b in zip(w0, w1))
     checksum = int(host_px[(NB - 1) % NFB][B - 1].sum())  # the read-back is real
 
     # ---- leg 3: per-kernel CUDA-event times (roofline of the dominant kernel)
