@@ -1638,7 +1638,7 @@ int32_t grb_draw_present(grb_context *ctx, grb_framebuffer *fb, int32_t frame0, 
             }
             if (e != cudaSuccess) return fail(ctx, GRB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
             hit = new GraphEntry;
-            hit->key = key;
+            std::memcpy(&hit->key, &key, sizeof key);   // byte image, padding included: the cache compares with memcmp
             hit->launches = launches;
             const cudaError_t ei = cudaGraphInstantiate(&hit->exec, graph, 0);
             cudaGraphDestroy(graph);
