@@ -26,6 +26,7 @@ GRB_OPT_SHOW_EDGES = 1 << 6
 GRB_OPT_SHOW_VERTICES = 1 << 7
 GRB_OPT_CROSSHAIR = 1 << 8
 GRB_OPT_FOG = 1 << 9
+GRB_OPT_AFFINE_TEXTURES = 1 << 10
 GRB_OPT_DEFAULT = (GRB_OPT_FRUSTUM_CLIPPING | GRB_OPT_SHOW_FACES | GRB_OPT_BACKFACE_CULLING |
                    GRB_OPT_LIGHTING | GRB_OPT_SHOW_TEXTURES)
 GRB_TILE = 32

@@ -772,8 +772,12 @@ __global__ void __launch_bounds__(kRasterThreads, kRasterBlocksPerSM) raster_ker
                 const float u0z0 = fdiv(uv.u0, r.w0), v0z0 = fdiv(uv.v0, r.w0);
                 const float u1z1 = fdiv(uv.u1, r.w1), v1z1 = fdiv(uv.v1, r.w1);
                 const float u2z2 = fdiv(uv.u2, r.w2), v2z2 = fdiv(uv.v2, r.w2);
-                const float u = fdiv(fadd(fadd(fmul(al, u0z0), fmul(be, u1z1)), fmul(ga, u2z2)), z);
-                const float v = fdiv(fadd(fadd(fmul(al, v0z0), fmul(be, v1z1)), fmul(ga, v2z2)), z);
+                float u = fdiv(fadd(fadd(fmul(al, u0z0), fmul(be, u1z1)), fmul(ga, u2z2)), z);
+                float v = fdiv(fadd(fadd(fmul(al, v0z0), fmul(be, v1z1)), fmul(ga, v2z2)), z);
+                if (a.options & GRB_OPT_AFFINE_TEXTURES) {   // not a reference code path: include/gorender_b200.h
+                    u = -fadd(fadd(fmul(al, uv.u0), fmul(be, uv.u1)), fmul(ga, uv.u2));
+                    v = -fadd(fadd(fmul(al, uv.v0), fmul(be, uv.v1)), fmul(ga, uv.v2));
+                }
                 c = sample_texture(t, u, v);
             }
         }

@@ -398,6 +398,9 @@ class Renderer:
         self.Fog = False
         self.FogStart, self.FogEnd = np.float32(0.100), np.float32(0.033)
         self.FogColor = (100, 100, 100, 255)
+        # README.md:46 lists "Affine texture mapping"; the reference has no code path for it.  This repository's
+        # own, unpinned definition (include/gorender_b200.h, GRB_OPT_AFFINE_TEXTURES); off by default
+        self.AffineTextures = False
         # renderer.go:144,151: numTiles is 1 when !parallel, else max(NumCPU, 16) (16 on any
         # host the reference runs on: more than 16 CPUs panic)
         self.numTiles = 16 if parallel else 1
@@ -416,6 +419,7 @@ class Renderer:
         if self.ShowVertices: o |= _cabi.GRB_OPT_SHOW_VERTICES
         if self.CrossHair: o |= _cabi.GRB_OPT_CROSSHAIR
         if self.Fog: o |= _cabi.GRB_OPT_FOG
+        if self.AffineTextures: o |= _cabi.GRB_OPT_AFFINE_TEXTURES
         return o
 
     def draw_params(self, rows: Optional[Tuple[int, int]] = None) -> _cabi.grb_draw_params:

@@ -59,6 +59,13 @@ enum {
      * (`!demoMode`, main.go:22; the Fog call is commented out); here they are option bits. */
     GRB_OPT_CROSSHAIR        = 1u << 8,   /* FrameBuffer.CrossHair({255,255,0,255}), rasterizer.go:209-217 */
     GRB_OPT_FOG              = 1u << 9,   /* FrameBuffer.Fog(fog_start, fog_end, fog_color), rasterizer.go:193-207 */
+    /* Affine texture mapping.  NOT a reference code path: README.md:46 lists it and BASELINE.json's north_star names it,
+     * but rasterizer.go:158-159 (perspective-correct) is the only interpolation the reference has, so there is nothing
+     * to be identical to — this mode is UNPINNED by construction.  Definition used here: the reference's expression with
+     * the 1/w factors and the division by zRec removed, i.e. linear in screen space with the reference's own (biased)
+     * barycentric weights, u = -((alpha*u0 + beta*u1) + gamma*u2), v likewise; the sign keeps Texture.Sample's
+     * convention (the reference's u, v come out negated).  Off by default; depth is unaffected. */
+    GRB_OPT_AFFINE_TEXTURES  = 1u << 10,
     GRB_OPT_DEFAULT = GRB_OPT_FRUSTUM_CLIPPING | GRB_OPT_SHOW_FACES |
                       GRB_OPT_BACKFACE_CULLING | GRB_OPT_LIGHTING |
                       GRB_OPT_SHOW_TEXTURES

@@ -393,6 +393,7 @@ struct FrameBuffer {
     std::vector<float> z;
     std::vector<RGBA> pix;
     int64_t writes = 0;  // diagnostic: number of z-test passes (serial mode only)
+    bool affine = false; // ORC_OPT_AFFINE_TEXTURES (not in the reference, see gorender_oracle.h)
 
     // rasterizer.go:36-44
     void clear(RGBA c) {
@@ -521,6 +522,10 @@ void fb_triangle(FrameBuffer &fb,
                 if (zrec >= fb.z[index]) {
                     float u = (alpha * u0z0 + beta * u1z1 + gamma * u2z2) / zrec;
                     float v = (alpha * v0z0 + beta * v1z1 + gamma * v2z2) / zrec;
+                    if (fb.affine) {   // screen-space linear interpolation; the sign keeps Texture.Sample's convention (H6)
+                        u = -(alpha * u0 + beta * u1 + gamma * u2);
+                        v = -(alpha * v0 + beta * v1 + gamma * v2);
+                    }
                     float intensity = alpha * ia + beta * ib + gamma * ic;
                     RGBA c = kFaceColor;
                     if (tex != nullptr) c = texture_sample(*tex, u, v);
@@ -889,6 +894,7 @@ int32_t orc_renderer_draw(orc_renderer *r, const orc_mesh *meshes, int32_t nmesh
     r->screen = load_m4(screen);
     r->light = {light[0], light[1], light[2]};
     r->options = options;
+    r->fb.affine = (options & ORC_OPT_AFFINE_TEXTURES) != 0;
     r->recorded.clear();
     r->visibility.assign(nobj, ORC_BOX_OUTSIDE);
     if ((int)r->scratch.size() < nobj) r->scratch.resize(nobj);

@@ -42,6 +42,10 @@ enum {
     ORC_OPT_SHOW_VERTICES    = 1u << 7,   /* renderer.go:212-216 */
     ORC_OPT_CROSSHAIR        = 1u << 8,   /* renderer.go:476-478 (`!demoMode`, a constant in main.go:22) */
     ORC_OPT_FOG              = 1u << 9,   /* renderer.go:479 (commented out in the reference) */
+    /* NOT in the reference: README.md:46 lists "Affine texture mapping" but no code path exists.  The mode
+     * restated here is this repository's own definition (include/gorender_b200.h, GRB_OPT_AFFINE_TEXTURES): rasterizer.go:158-159
+     * with the 1/w factors and the division by zRec removed.  There is nothing of the reference to pin it against. */
+    ORC_OPT_AFFINE_TEXTURES  = 1u << 10,
     ORC_OPT_DEFAULT = ORC_OPT_FRUSTUM_CLIPPING | ORC_OPT_SHOW_FACES |
                       ORC_OPT_BACKFACE_CULLING | ORC_OPT_LIGHTING |
                       ORC_OPT_SHOW_TEXTURES /* renderer.go:130-137 */

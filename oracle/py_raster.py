@@ -140,6 +140,9 @@ class FrameBuffer:
                         if zrec >= self.ZBuffer[index]:
                             u = f32(f32(f32(f32(alpha * u0z0) + f32(beta * u1z1)) + f32(gamma * u2z2)) / zrec)
                             v = f32(f32(f32(f32(alpha * v0z0) + f32(beta * v1z1)) + f32(gamma * v2z2)) / zrec)
+                            if self.affine:   # not in the reference (gorender_oracle.h, ORC_OPT_AFFINE_TEXTURES)
+                                u = f32(-f32(f32(f32(alpha * u0) + f32(beta * u1)) + f32(gamma * u2)))
+                                v = f32(-f32(f32(f32(alpha * v0) + f32(beta * v1)) + f32(gamma * v2)))
                             intensity = f32(f32(f32(alpha * ia) + f32(beta * ib)) + f32(gamma * ic))
                             c = FACE_COLOR
                             if texture is not None:
@@ -195,11 +198,12 @@ def tile_boundaries(tile: int, num_tiles: int, width: int, height: int):   # ren
 
 def draw(width: int, height: int, num_tiles: int, triangles, textures, *, ShowFaces=True, ShowEdges=False,
          ShowVertices=False, ShowTextures=True, CrossHair=False, Fog=False, FogStart=0.100, FogEnd=0.033,
-         FogColor=(100, 100, 100, 255)):
+         FogColor=(100, 100, 100, 255), AffineTextures=False):
     """Renderer.Draw from the barrier between the two phases on (renderer.go:448-449, 461-482), serial branch.
     `triangles`: records with fields points (3,4), uvs (3,2), intensity (3,), tex — the oracle's recording, in
     submission order.  Returns (pixels (H,W,4) uint8, zbuffer (H,W) float32, TPF)."""
     fb = FrameBuffer(width, height)
+    fb.affine = bool(AffineTextures)
     fb.Clear((50, 50, 50, 255))
     fb.DotGrid((100, 100, 100, 255), 10)
     bounds = [tile_boundaries(i, num_tiles, width, height) for i in range(num_tiles)]

@@ -225,4 +225,8 @@ PINNED: Dict[str, Callable[[], SceneDef]] = {
     "fog_c1_custom": lambda: c1(640, 360, Fog=True, FogStart=np.float32(0.25), FogEnd=np.float32(0.17),
                                 FogColor=(10, 200, 90, 128)),
     "fog_wire_gouraud": lambda: gouraud_sphere(ShowEdges=True, Fog=True, FogStart=np.float32(0.7), FogEnd=np.float32(0.4)),
+    # affine texture mapping: this repository's own definition (GRB_OPT_AFFINE_TEXTURES) — no code path in the reference
+    "affine_c2_poseB": lambda: c2("B", AffineTextures=True),
+    "affine_gouraud_textured": lambda: gouraud_sphere(AffineTextures=True),
+    "affine_npot_wire": lambda: npot_texture(AffineTextures=True, ShowEdges=True),
 }

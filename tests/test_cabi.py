@@ -76,7 +76,7 @@ def test_option_bits_match_header():
     src = open(os.path.join(ROOT, "include", "gorender_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     bits = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"\b(GRB_OPT_[A-Z_]+)\s*=\s*1u\s*<<\s*(\d+)", src)}
-    assert len(bits) == 10
+    assert len(bits) == 11
     for name, value in bits.items():
         assert getattr(_cabi, name) == value, name
     orc = open(os.path.join(ROOT, "oracle", "gorender_oracle.h")).read()

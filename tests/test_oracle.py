@@ -293,3 +293,33 @@ def test_go_harness_scene_export_round_trips(oracle, tmp_path):
         want = oracle.draw(want_sc.renderer(None), want_sc.objects, want_sc.camera)
         assert got["tpf"] == want["tpf"], s["name"]
         assert np.array_equal(got["pixels"], want["pixels"]) and np.array_equal(got["zbuffer"].view(np.uint32), want["zbuffer"].view(np.uint32)), s["name"]
+
+
+def test_affine_mode_is_the_perspective_one_where_w_is_constant(oracle):
+    """GRB_OPT_AFFINE_TEXTURES is this repository's own definition (the reference lists the feature, README.md:46, but has no
+    code path).  Sanity of that definition: on a quad parallel to the screen (constant clip w) it samples the same texels as the
+    reference's perspective-correct interpolation up to float rounding at texel borders, depth is untouched, and on a tilted
+    quad the two differ — which is all "affine" means."""
+    tex = workloads.checker_texture(64)
+    verts = np.array([[-1, -1, 0, 1], [1, -1, 0, 1], [1, 1, 0, 1], [-1, 1, 0, 1]], np.float32)
+    uv = np.array([[[0, 0], [1, 0], [1, 1]], [[0, 0], [1, 1], [0, 1]]], np.float32)
+    faces = g.FaceArray(np.array([[0, 1, 2], [0, 2, 3]], np.int32), None, uv, np.zeros(2, np.int32), [tex])
+    mesh = g.NewMesh(verts, None, faces)
+
+    def render(rot_x, affine):
+        o = g.NewObject(mesh)
+        o.Rotation = np.array([rot_x, 0, 0], np.float32)
+        sc = scene_defs.SceneDef(320, 240, [o], g.Camera(Position=(0, 0, 3)), {"AffineTextures": affine, "Lighting": False})
+        return oracle.draw(sc.renderer(None), sc.objects, sc.camera)
+
+    flat_p, flat_a = render(0.0, False), render(0.0, True)
+    assert np.array_equal(flat_p["zbuffer"].view(np.uint32), flat_a["zbuffer"].view(np.uint32))
+    covered = flat_p["zbuffer"] > -1
+    assert covered.sum() > 10000
+    differ = (flat_p["pixels"] != flat_a["pixels"]).any(axis=-1)
+    assert differ.sum() < 0.02 * covered.sum()          # only pixels whose (u, v) sits on a texel border
+    tilt_p, tilt_a = render(1.0, False), render(1.0, True)
+    assert np.array_equal(tilt_p["zbuffer"].view(np.uint32), tilt_a["zbuffer"].view(np.uint32))
+    covered = tilt_p["zbuffer"] > -1
+    differ = (tilt_p["pixels"] != tilt_a["pixels"]).any(axis=-1)
+    assert differ.sum() > 0.2 * covered.sum()

@@ -50,6 +50,10 @@ CASES = {
     "npot_texture_cube": lambda: scene_defs.SceneDef(90, 60, [scene_defs._obj(textured_npot_cube(), r=(0.3, 0.6, 0.1))],
                                                      g.Camera(Position=(0.9, 0.2, 1.4)), {}),
     "no_textures": lambda: small(scene_defs.c2, 64, 48, pose="B", ShowTextures=False, ShowVertices=True),
+    # the affine mode is this repository's own definition (no code path in the reference): both restatements must agree on it
+    "affine_cube_poseB": lambda: small(scene_defs.c2, 96, 54, pose="B", AffineTextures=True),
+    "affine_npot_cube": lambda: scene_defs.SceneDef(90, 60, [scene_defs._obj(textured_npot_cube(), r=(0.3, 0.6, 0.1))],
+                                                    g.Camera(Position=(0.9, 0.2, 1.4)), {"AffineTextures": True}),
 }
 
 
@@ -70,7 +74,8 @@ def test_oracle_matches_python_restatement(name, oracle):
     px, z, tpf = py_raster.draw(sc.width, sc.height, r.numTiles, ref["triangles"], textures,
                                 ShowFaces=r.ShowFaces, ShowEdges=r.ShowEdges, ShowVertices=r.ShowVertices,
                                 ShowTextures=r.ShowTextures, CrossHair=r.CrossHair, Fog=r.Fog,
-                                FogStart=r.FogStart, FogEnd=r.FogEnd, FogColor=tuple(r.FogColor))
+                                FogStart=r.FogStart, FogEnd=r.FogEnd, FogColor=tuple(r.FogColor),
+                                AffineTextures=r.AffineTextures)
     assert tpf == ref["tpf"]
     assert np.array_equal(z.view(np.uint32), ref["zbuffer"].view(np.uint32)), name
     same = (px == ref["pixels"]).all(axis=-1)
@@ -123,7 +128,8 @@ def test_whole_draw_restated_in_python(name, variant, oracle):
     px, z, tpf = py_raster.draw(sc.width, sc.height, r.numTiles, tris, textures,
                                 ShowFaces=r.ShowFaces, ShowEdges=r.ShowEdges, ShowVertices=r.ShowVertices,
                                 ShowTextures=r.ShowTextures, CrossHair=r.CrossHair, Fog=r.Fog,
-                                FogStart=r.FogStart, FogEnd=r.FogEnd, FogColor=tuple(r.FogColor))
+                                FogStart=r.FogStart, FogEnd=r.FogEnd, FogColor=tuple(r.FogColor),
+                                AffineTextures=r.AffineTextures)
     assert tpf == ref["tpf"]
     assert np.array_equal(z.view(np.uint32), ref["zbuffer"].view(np.uint32))
     assert np.array_equal(px, ref["pixels"])
