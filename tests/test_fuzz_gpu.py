@@ -76,6 +76,8 @@ def test_random_scene(seed, device, oracle):
         r.CrossHair = bool(orng.random() < 0.5)
         r.Fog = bool(orng.random() < 0.4)
         r.FogStart, r.FogEnd = np.float32(orng.uniform(0.3, 1.0)), np.float32(orng.uniform(0.05, 0.3))
+    if seed % 4 == 1:
+        r.AffineTextures = True      # this repository's own mode (no reference code path): CUDA and oracle must still agree
     r.Draw(objs, cam)
     ref = oracle.draw(r, objs, cam)
     assert int(r.last_stats["out_of_domain"][0]) == 0
