@@ -46,6 +46,7 @@ type cudaRenderer struct {
 	// place once (grb_host_register; Go's collector does not move heap objects), after which a Draw moves
 	// only the 32x32 tiles that changed instead of 7.4 MB per 720p frame.
 	mirrors map[unsafe.Pointer]*C.grb_mirror
+	pins    runtimePinner // the mirrored slices stay pinned (runtime.Pinner) for as long as the library holds their address
 	pending *C.grb_mirror // colour mirror of a DrawAsync still in flight
 }
 
@@ -188,6 +189,9 @@ func (s *cudaRenderer) mirror(r *Renderer, p unsafe.Pointer, bytes int, plane C.
 	if m, ok := s.mirrors[p]; ok {
 		return m
 	}
+	// the library keeps this address beyond the call (the GPU writes tiles into the slice on every Draw): cgo allows that
+	// only for pinned Go memory, so the slice is pinned for the renderer's lifetime, and page-locked for the device
+	s.pins.ptr(p)
 	if rc := C.grb_host_register(p, C.uint64_t(bytes)); rc != C.GRB_OK {
 		panic("gorender_b200: grb_host_register failed (cannot pin the framebuffer slice)")
 	}

@@ -85,3 +85,50 @@ def test_option_bits_match_header():
     assert {("GRB_OPT_" + k): v for k, v in obits.items()} == bits     # tests feed Renderer.options() to both sides
     assert int(re.search(r"#define GRB_ABI_VERSION (\d+)", src).group(1)) == _cabi.GRB_ABI_VERSION
     assert int(re.search(r"#define GRB_TILE (\d+)", src).group(1)) == _cabi.GRB_TILE
+
+
+def test_go_shim_uses_only_what_the_header_declares():
+    """The cgo shim cannot be compiled here (no Go toolchain), so at least every C identifier it touches must exist in the
+    header it is written against, with the number of arguments the header declares, and its braces must balance."""
+    hdr = open(os.path.join(ROOT, "include", "gorender_b200.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(grb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr_nc, flags=re.S):
+        args = m.group(2).strip()
+        decls[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    consts = set(re.findall(r"\b(GRB_[A-Z0-9_]+)\b", hdr_nc))
+    types = set(re.findall(r"\btypedef struct (grb_[a-z_]+)", hdr_nc)) | set(re.findall(r"}\s*(grb_[a-z_]+)\s*;", hdr_nc))
+    go_dir = os.path.join(ROOT, "go")
+    seen_calls = 0
+    for fn in sorted(os.listdir(go_dir)):
+        if not fn.endswith(".go"):
+            continue
+        src = open(os.path.join(go_dir, fn)).read()
+        code = re.sub(r"//[^\n]*", "", re.sub(r"/\*.*?\*/", "", src, flags=re.S))
+        assert code.count("{") == code.count("}"), fn
+        assert code.count("(") == code.count(")"), fn
+        for name in set(re.findall(r"\bC\.(GRB_[A-Z0-9_]+)\b", code)):
+            assert name in consts, f"{fn}: C.{name} is not in the header"
+        for name in set(re.findall(r"\bC\.(grb_[a-z0-9_]+)\b", code)):
+            assert name in decls or name in types, f"{fn}: C.{name} is not in the header"
+        # calls: count top-level commas between the parentheses
+        for m in re.finditer(r"\bC\.(grb_[a-z0-9_]+)\(", code):
+            name = m.group(1)
+            if name not in decls:
+                continue
+            depth, i, commas, empty = 1, m.end(), 0, True
+            while depth:
+                ch = code[i]
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    commas += 1
+                if depth and not ch.isspace():
+                    empty = False
+                i += 1
+            nargs = 0 if empty else commas + 1
+            assert nargs == decls[name], f"{fn}: C.{name} called with {nargs} arguments, the header declares {decls[name]}"
+            seen_calls += 1
+    assert seen_calls >= 12
